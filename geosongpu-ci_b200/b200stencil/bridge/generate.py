@@ -1,0 +1,372 @@
+"""YAML -> C-ABI generator for libb200stencil.
+
+Plays the role of the reference's ``tcn-fpy`` generator
+(/root/reference/src/tcn/py_ftn_interface/cli.py:80-136, bridge.py:30-184) with the call
+direction reversed: there Fortran calls *into* Python through generated C glue
+(templates/interface.c.jinja2:8-30); here Python (or Fortran, through the same
+``bind(c)`` symbols) calls *into* CUDA.  One YAML file, in the reference's schema
+(argument.py:6-98), is the single source of truth for
+
+* ``include/b200stencil.h``  - the C prototypes (``emit_header``),
+* the cffi ``cdef`` the host package loads the library with (``emit_cdef``),
+* the argument marshalling tables (``Bridge.functions``),
+* a Fortran ``bind(c)`` interface module (``emit_fortran``, cf. templates/interface.f90.jinja2:1-56).
+
+CLI:  python -m b200stencil.bridge.generate [DEF.yaml] [--header OUT.h] [--fortran OUT.f90]
+"""
+from __future__ import annotations
+
+import argparse
+import os
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import yaml
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_YAML = os.path.join(HERE, "b200stencil.yaml")
+REPO_ROOT = os.path.abspath(os.path.join(HERE, "..", "..", ".."))
+DEFAULT_HEADER = os.path.join(REPO_ROOT, "include", "b200stencil.h")
+DEFAULT_GLUE = os.path.abspath(os.path.join(HERE, "..", "..", "csrc", "abi_glue.inc"))
+
+PRECISIONS = {"double": ("double", "int64_t", ""), "float": ("float", "int32_t", "_f32")}
+
+_SCALARS = {"int": "int", "float": "float", "double": "double", "int64": "int64_t"}
+_ARRAYS = {"array_int": "int", "array_float": "float", "array_double": "double", "array_int64": "int64_t"}
+_F90_SCALARS = {
+    "int": "integer(kind=c_int), value",
+    "float": "real(kind=c_float), value",
+    "double": "real(kind=c_double), value",
+    "int64_t": "integer(kind=c_int64_t), value",
+}
+
+
+@dataclass
+class Argument:
+    """One YAML ``!Argument`` (reference: argument.py:6-86)."""
+
+    name: str
+    type: str
+    dims: Optional[int] = None
+    intent: str = "in"  # in | inout | out, from the YAML section it sits in
+
+    @property
+    def name_sanitize(self) -> str:  # reference: argument.py:16-20
+        return f"_{self.name}" if self.name in ("is", "in") else self.name
+
+    @property
+    def is_array(self) -> bool:
+        return self.type.startswith("array_")
+
+    @property
+    def is_precision_dependent(self) -> bool:
+        return self.type in ("real", "array_real", "array_index")
+
+    def element_ctype(self, precision: str) -> str:
+        real, index, _ = PRECISIONS[precision]
+        if self.type in ("real", "array_real"):
+            return real
+        if self.type == "array_index":
+            return index
+        if self.type in _SCALARS:
+            return _SCALARS[self.type]
+        if self.type in _ARRAYS:
+            return _ARRAYS[self.type]
+        if self.type == "MPI":  # kept for schema compatibility (argument.py:58-59)
+            return "void*"
+        raise RuntimeError(f"ERROR_DEF_TYPE_TO_C: {self.type}")
+
+    def stride_names(self) -> List[str]:
+        if not self.is_array:
+            return []
+        return {3: ["sj", "sk", "sb"], 2: ["sj", "sb"]}.get(self.dims or 1, [])
+
+    def c_parameters(self, precision: str) -> List[str]:
+        t = self.element_ctype(precision)
+        if not self.is_array:
+            return [f"{t} {self.name}"]
+        const = "const " if self.intent == "in" else ""
+        return [f"{const}{t}* {self.name}"] + [f"int64_t {self.name}_{s}" for s in self.stride_names()]
+
+
+@dataclass
+class Function:
+    """One bridge entry (reference: base.py:9-40)."""
+
+    name: str
+    inputs: List[Argument] = field(default_factory=list)
+    inouts: List[Argument] = field(default_factory=list)
+    outputs: List[Argument] = field(default_factory=list)
+    cites: str = ""
+
+    @property
+    def arguments(self) -> List[Argument]:  # reference order: base.py:35-36
+        return self.inputs + self.inouts + self.outputs
+
+    @property
+    def is_precision_dependent(self) -> bool:
+        return any(a.is_precision_dependent for a in self.arguments)
+
+    def precisions(self) -> List[str]:
+        return list(PRECISIONS) if self.is_precision_dependent else ["double"]
+
+    def symbol(self, prefix: str, precision: str) -> str:
+        return f"{prefix}_{self.name}{PRECISIONS[precision][2]}_c"
+
+    def c_prototype(self, prefix: str, precision: str) -> str:
+        params: List[str] = []
+        for a in self.arguments:
+            params += a.c_parameters(precision)
+        params.append("void* stream")
+        return f"int {self.symbol(prefix, precision)}({', '.join(params)});"
+
+
+def _argument_constructor(loader, node):
+    return dict(loader.construct_mapping(node))
+
+
+class _Loader(yaml.SafeLoader):
+    pass
+
+
+_Loader.add_constructor("!Argument", _argument_constructor)  # reference: argument.py:89-98
+
+
+class Bridge:
+    """Parsed bridge definition (reference: Bridge.make_from_yaml, bridge.py:30-62)."""
+
+    def __init__(self, prefix: str, functions: List[Function]):
+        self.prefix = prefix
+        self.functions: Dict[str, Function] = {f.name: f for f in functions}
+
+    @classmethod
+    def from_yaml(cls, path: str = DEFAULT_YAML) -> "Bridge":
+        with open(path) as f:
+            defs = yaml.load(f, Loader=_Loader)
+        if defs.get("type") != "py_ftn_interface":
+            raise RuntimeError(f"{path}: not a py_ftn_interface definition")
+        functions = []
+        for entry in defs["bridge"]:
+            args = entry.get("arguments")
+            if args in (None, "None"):
+                args = {}
+            fn = Function(entry["name"], cites=entry.get("cites", ""))
+            for section, intent, dest in (
+                ("inputs", "in", fn.inputs),
+                ("inouts", "inout", fn.inouts),
+                ("outputs", "out", fn.outputs),
+            ):
+                for a in args.get(section) or []:
+                    dest.append(Argument(intent=intent, **a))
+            functions.append(fn)
+        return cls(defs["name"], functions)
+
+    # ---- emitters -------------------------------------------------------------------------
+
+    def prototypes(self) -> List[str]:
+        out = []
+        for fn in self.functions.values():
+            for precision in fn.precisions():
+                out.append(fn.c_prototype(self.prefix, precision))
+        return out
+
+    def symbols(self) -> List[str]:
+        out = list(RUNTIME_SYMBOLS)
+        for fn in self.functions.values():
+            out += [fn.symbol(self.prefix, p) for p in fn.precisions()]
+        return out
+
+    def emit_cdef(self) -> str:
+        return RUNTIME_CDEF + "\n".join(self.prototypes()) + "\n"
+
+    def emit_header(self) -> str:
+        lines = [HEADER_PROLOGUE]
+        for fn in self.functions.values():
+            lines.append(f"/* {fn.name}: {fn.cites} */")
+            for precision in fn.precisions():
+                lines.append("B2S_API " + fn.c_prototype(self.prefix, precision))
+            lines.append("")
+        lines.append(HEADER_EPILOGUE)
+        return "\n".join(lines)
+
+    def emit_glue(self) -> str:
+        """``extern "C"`` definitions forwarding the flat arguments to ``b2s::impl::<fn><T>(...)``.
+
+        The CUDA sources include this file (csrc/abi_glue.inc), so a stencil implementation whose
+        signature drifts from the YAML fails to compile (the generated C shim of the reference,
+        templates/interface.c.jinja2:8-30, plays the same forwarding role).
+        """
+        out = ["// GENERATED by b200stencil/bridge/generate.py from b200stencil.yaml -- do not edit.", ""]
+        for fn in self.functions.values():
+            for precision in fn.precisions():
+                real, index, _ = PRECISIONS[precision]
+                params, call = [], []
+                for a in fn.arguments:
+                    params += a.c_parameters(precision)
+                    t = a.element_ctype(precision)
+                    if a.is_array and (a.dims or 1) >= 2:
+                        ct = f"const {t}" if a.intent == "in" else t
+                        strides = ", ".join(f"{a.name}_{s}" for s in a.stride_names())
+                        call.append(f"b2s::F{a.dims}<{ct}>{{{a.name}, {strides}}}")
+                    else:
+                        call.append(a.name)
+                params.append("void* stream")
+                call.append("static_cast<cudaStream_t>(stream)")
+                targ = f"<{real}>" if fn.is_precision_dependent else ""
+                out += [
+                    f'extern "C" int {fn.symbol(self.prefix, precision)}({", ".join(params)}) {{',
+                    f"  return b2s::impl::{fn.name}{targ}({', '.join(call)});",
+                    "}",
+                    "",
+                ]
+        return "\n".join(out)
+
+    def emit_fortran(self) -> str:
+        """``bind(c)`` interface module for Fortran callers (cf. templates/interface.f90.jinja2:1-56)."""
+        out = [
+            f"module {self.prefix}_interface_mod",
+            "   use iso_c_binding, only: c_int, c_int32_t, c_int64_t, c_float, c_double, c_ptr",
+            "   implicit none",
+            "   private",
+        ]
+        body = []
+        for fn in self.functions.values():
+            for precision in fn.precisions():
+                sym = fn.symbol(self.prefix, precision)
+                out.append(f"   public :: {sym}")
+                names, decls = [], []
+                for a in fn.arguments:
+                    t = a.element_ctype(precision)
+                    if a.is_array:
+                        # device pointers are opaque addresses on the Fortran side (type(c_ptr), value)
+                        names.append(a.name)
+                        decls.append(f"         type(c_ptr), value :: {a.name}")
+                        for s in a.stride_names():
+                            names.append(f"{a.name}_{s}")
+                            decls.append(f"         integer(kind=c_int64_t), value :: {a.name}_{s}")
+                    else:
+                        names.append(a.name)
+                        decls.append(f"         {_F90_SCALARS[t]} :: {a.name}")
+                names.append("stream")
+                decls.append("         type(c_ptr), value :: stream")
+                body += [
+                    f"      function {sym}({', '.join(names)}) bind(c, name='{sym}') result(status)",
+                    "         import c_int, c_int32_t, c_int64_t, c_float, c_double, c_ptr",
+                    *decls,
+                    "         integer(kind=c_int) :: status",
+                    f"      end function {sym}",
+                ]
+        out += ["   interface", *body, "   end interface", f"end module {self.prefix}_interface_mod", ""]
+        return "\n".join(out)
+
+
+RUNTIME_SYMBOLS = [
+    "b2s_init",
+    "b2s_finalize",
+    "b2s_device",
+    "b2s_last_error",
+    "b2s_abi_version",
+    "b2s_sm_count",
+    "b2s_set_option",
+    "b2s_get_option",
+    "b2s_launch_count",
+]
+
+RUNTIME_CDEF = """
+int b2s_init(int device);
+int b2s_finalize(void);
+int b2s_device(void);
+const char* b2s_last_error(void);
+int b2s_abi_version(void);
+int b2s_sm_count(void);
+int b2s_set_option(const char* name, int value);
+int b2s_get_option(const char* name);
+int64_t b2s_launch_count(void);
+"""
+
+HEADER_PROLOGUE = """/* b200stencil.h -- C-ABI of libb200stencil.so (GENERATED, do not edit).
+ *
+ * Generated by geosongpu-ci_b200/b200stencil/bridge/generate.py from
+ * geosongpu-ci_b200/b200stencil/bridge/b200stencil.yaml, which uses the schema of the
+ * reference's Fortran<->C<->Python bridge generator
+ * (/root/reference/src/tcn/py_ftn_interface/README.md:9-22, argument.py:54-86).
+ *
+ * What each entry point replaces: the reference reaches a stencil through
+ *   {prefix}_{fn}_f  -> bind(c) {prefix}_{fn}_c -> {prefix}_{fn}_py -> hook -> gt4py/NDSL stencil
+ * (templates/interface.f90.jinja2:26-39, interface.c.jinja2:8-30, interface.py.jinja2:26-51).
+ * Here {prefix}_{fn}_c *is* the stencil: a hand-written sm_100a kernel launch.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller; the library allocates nothing
+ *     persistent and performs no hidden host<->device copies;
+ *   - fields are i-fastest: a dims-3 argument x is followed by x_sj, x_sk, x_sb (strides in
+ *     elements of j, k and the tile/sub-domain batch axis b), a dims-2 argument by x_sj, x_sb;
+ *     the pointer addresses compute-domain cell (0,0,0) (halo cells sit at negative offsets);
+ *   - calls are asynchronous on `stream` (a cudaStream_t; NULL = the default stream);
+ *   - return value: 0 ok, < 0 argument/state error, > 0 a cudaError_t; b2s_last_error() gives
+ *     the message (thread-local).  The reference's void bridge has no error channel
+ *     (interface.c.jinja2:8, SURVEY.md 8b) -- this one does;
+ *   - {fn}_c computes in double (index outputs int64), {fn}_f32_c in float (index outputs int32).
+ */
+#ifndef B200STENCIL_H
+#define B200STENCIL_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2S_ABI_VERSION 1
+#if defined(__GNUC__)
+#define B2S_API __attribute__((visibility("default")))
+#else
+#define B2S_API
+#endif
+
+/* runtime: init / finalize triple of the GEOS bridge (example_def_dycore.yaml:4,21,71) */
+B2S_API int b2s_init(int device);
+B2S_API int b2s_finalize(void);
+/* device bound by b2s_init, -1 before */
+B2S_API int b2s_device(void);
+B2S_API const char* b2s_last_error(void);
+B2S_API int b2s_abi_version(void);
+B2S_API int b2s_sm_count(void);
+/* tuning knobs (kernel variant selection for benchmarking); unknown names return -1 */
+B2S_API int b2s_set_option(const char* name, int value);
+B2S_API int b2s_get_option(const char* name);
+/* number of kernels this library has launched in this process (bench.py gpu_launches) */
+B2S_API int64_t b2s_launch_count(void);
+"""
+
+HEADER_EPILOGUE = """#ifdef __cplusplus
+}
+#endif
+#endif /* B200STENCIL_H */
+"""
+
+
+def main(argv=None) -> int:
+    ap = argparse.ArgumentParser(description=__doc__.split("\n\n")[0])
+    ap.add_argument("definition", nargs="?", default=DEFAULT_YAML)
+    ap.add_argument("--header", default=DEFAULT_HEADER)
+    ap.add_argument("--glue", default=DEFAULT_GLUE)
+    ap.add_argument("--fortran", default=None)
+    ap.add_argument("--check", action="store_true", help="fail if the header on disk is stale")
+    ns = ap.parse_args(argv)
+    bridge = Bridge.from_yaml(ns.definition)
+    text = bridge.emit_header()
+    if ns.check:
+        with open(ns.header) as f:
+            return 0 if f.read() == text else 1
+    os.makedirs(os.path.dirname(ns.header), exist_ok=True)
+    with open(ns.header, "w") as f:
+        f.write(text)
+    with open(ns.glue, "w") as f:
+        f.write(bridge.emit_glue())
+    if ns.fortran:
+        with open(ns.fortran, "w") as f:
+            f.write(bridge.emit_fortran())
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())

@@ -1,0 +1,124 @@
+"""Stencil entry points on device fields (torch CUDA tensors, i-fastest; see fields.py).
+
+One function per row of SURVEY.md 8(a).  Argument names and order follow the reference stencil
+signatures where a reference exists (dsl_patterns/*.py) and the oracle spec otherwise.  Every
+function only validates, marshals and calls the C-ABI (``_abi.call``); the arithmetic is in
+csrc/*.cu.  Fields may carry a leading batch axis ``b`` (tiles / sub-domains).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _abi
+from .fields import shape3
+
+FV_HALO = 3
+
+
+def _index_dtype(t: torch.Tensor) -> torch.dtype:
+    return torch.int64 if t.dtype == torch.float64 else torch.int32
+
+
+def top_of_column(PLEmb, PLEmb_top, out_field, stream: Optional[int] = None) -> None:
+    """dsl_patterns/Do__get_top_of_the_column.py:33-38 -- K1 (csrc/k_patterns.cu)."""
+    ni, nj, nk, nb = shape3(PLEmb)
+    _abi.call(
+        "top_of_column", _abi.precision_of(PLEmb),
+        dict(ni=ni, nj=nj, nk=nk, nb=nb, PLEmb=PLEmb, PLEmb_top=PLEmb_top, out_field=out_field), stream,
+    )  # fmt: skip
+
+
+def while_in_function(in_field, out_field, threshold: float = 4.0, undefined_count=None, stream=None) -> None:
+    """dsl_patterns/Do__while_in_gt_functions.py:22-32 -- K2.
+
+    ``undefined_count`` (optional int64 device tensor of one element, caller-zeroed) receives the
+    number of points whose search ran off the column (undefined behaviour in the reference).
+    """
+    ni, nj, nk, nb = shape3(in_field)
+    _abi.call(
+        "while_in_function", _abi.precision_of(in_field),
+        dict(ni=ni, nj=nj, nk=nk, nb=nb, threshold=float(threshold), in_field=in_field, out_field=out_field,
+             undefined_count=undefined_count), stream,
+    )  # fmt: skip
+
+
+def hybrid_index_2dout(data_field, k_mask, k_index_desired, out_field, stream=None) -> None:
+    """dsl_patterns/WIP__hybrid_index_2dout.py:34-42 -- K3."""
+    ni, nj, nk, nb = shape3(data_field)
+    _abi.call(
+        "hybrid_index_2dout", _abi.precision_of(data_field),
+        dict(ni=ni, nj=nj, nk=nk, nb=nb, data_field=data_field, k_mask=k_mask, k_index_desired=k_index_desired,
+             out_field=out_field), stream,
+    )  # fmt: skip
+
+
+def find_klcl(PLmb, PLCL, KLCL, PLmb_at_KLCL, stream=None) -> None:
+    """S4a (spec: oracle/numpy_oracle.py find_klcl) -- K4a (csrc/k_moist.cu)."""
+    ni, nj, nk, nb = shape3(PLmb)
+    _abi.call(
+        "find_klcl", _abi.precision_of(PLmb),
+        dict(ni=ni, nj=nj, nk=nk, nb=nb, PLmb=PLmb, PLCL=PLCL, PLmb_at_KLCL=PLmb_at_KLCL, KLCL=KLCL), stream,
+    )  # fmt: skip
+
+
+def saturation_adjust(T, q, ql, p, stream=None) -> None:
+    """S4b (spec: oracle/numpy_oracle.py saturation_adjust) -- K4b; in place on T, q, ql."""
+    ni, nj, nk, nb = shape3(T)
+    _abi.call("saturation_adjust", _abi.precision_of(T), dict(ni=ni, nj=nj, nk=nk, nb=nb, p=p, T=T, q=q, ql=ql), stream)
+
+
+def cloud_top(ql, ktop, ql_min: float = 1.0e-8, stream=None) -> None:
+    """S4c (spec: oracle/numpy_oracle.py cloud_top) -- K4c."""
+    ni, nj, nk, nb = shape3(ql)
+    _abi.call("cloud_top", _abi.precision_of(ql), dict(ni=ni, nj=nj, nk=nk, nb=nb, ql_min=float(ql_min), ql=ql, ktop=ktop), stream)
+
+
+def fv_tp2d(q, crx, xfx, cry, yfx, rarea, q_out, region=None, q_out_halo: int = 0, stream=None) -> None:
+    """S5 (spec: oracle/numpy_oracle.py fv_tp2d) -- K5 (csrc/k_fv*.cu).
+
+    ``q`` carries a 3-cell halo on every horizontal side ([b,] ni+6, nj+6, nk); ``q_out`` is
+    compute-domain shaped, or halo-padded like ``q`` when ``q_out_halo`` = 3 (time stepping).
+    ``region`` = (i0, i1, j0, j1) restricts the update to a sub-rectangle (interior / boundary
+    split for halo-exchange overlap); default is the whole domain.
+    """
+    h = FV_HALO
+    nip, njp, nk, nb = shape3(q)
+    ni, nj = nip - 2 * h, njp - 2 * h
+    i0, i1, j0, j1 = (0, ni, 0, nj) if region is None else region
+    _abi.call(
+        "fv_tp2d", _abi.precision_of(q),
+        dict(ni=ni, nj=nj, nk=nk, nb=nb, i0=i0, i1=i1, j0=j0, j1=j1, q=q, crx=crx, xfx=xfx, cry=cry, yfx=yfx,
+             rarea=rarea, q_out=q_out),
+        stream, origins={"q": (h, h, 0), "q_out": (q_out_halo, q_out_halo, 0)},
+    )  # fmt: skip
+
+
+def pe_prefix(delp, ptop: float, pe, stream=None) -> None:
+    """S6a (spec: oracle/numpy_oracle.py pe_prefix) -- K6a (csrc/k_vertical.cu); pe has nk+1 levels."""
+    ni, nj, nk, nb = shape3(delp)
+    _abi.call("pe_prefix", _abi.precision_of(delp), dict(ni=ni, nj=nj, nk=nk, nb=nb, ptop=float(ptop), delp=delp, pe=pe), stream)
+
+
+def remap(pe1, q1, pe2, q2, stream=None) -> None:
+    """S6b (spec: oracle/numpy_oracle.py remap_column) -- K6b."""
+    ni, nj, nk1, nb = shape3(q1)
+    nk2 = shape3(q2)[2]
+    _abi.call("remap", _abi.precision_of(q1), dict(ni=ni, nj=nj, nk1=nk1, nk2=nk2, nb=nb, pe1=pe1, q1=q1, pe2=pe2, q2=q2), stream)
+
+
+def tridiag(a, b, c, d, x, w=None, stream=None) -> None:
+    """S6c (spec: oracle/numpy_oracle.py tridiag) -- K6c; ``w`` is scratch shaped like ``x``."""
+    ni, nj, nk, nb = shape3(b)
+    if w is None:
+        w = torch.empty_like(x)
+    _abi.call("tridiag", _abi.precision_of(b), dict(ni=ni, nj=nj, nk=nk, nb=nb, a=a, b=b, c=c, d=d, w=w, x=x), stream)
+
+
+def halo_move(links, nk: int, src, dst, stream=None) -> None:
+    """K7 (csrc/k_halo.cu): run the affine strip copies described by ``links`` (int64 [nlinks, 10])."""
+    nlinks = int(links.shape[0])
+    if nlinks == 0:
+        return
+    _abi.call("halo_move", _abi.precision_of(src), dict(nlinks=nlinks, nk=int(nk), links=links, src=src, dst=dst), stream)

@@ -1,0 +1,41 @@
+// K5 fv_tp2d dispatch: argument checks and variant selection (direct vs TMA-pipelined).
+#include "impl.cuh"
+
+namespace b2s {
+namespace impl {
+
+template <typename T>
+int fv_tp2d_direct(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j1, F3<const T> q, F3<const T> crx,
+                   F3<const T> xfx, F3<const T> cry, F3<const T> yfx, F2<const T> rarea, F3<T> q_out, cudaStream_t s);
+template <typename T>
+int fv_tp2d_tma(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j1, F3<const T> q, F3<const T> crx,
+                F3<const T> xfx, F3<const T> cry, F3<const T> yfx, F2<const T> rarea, F3<T> q_out, cudaStream_t s,
+                bool* applicable);
+
+template <typename T>
+int fv_tp2d(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j1, F3<const T> q, F3<const T> crx,
+            F3<const T> xfx, F3<const T> cry, F3<const T> yfx, F2<const T> rarea, F3<T> q_out, cudaStream_t s) {
+  B2S_ARGCHECK(ni > 0 && nj > 0 && nk > 0 && nb > 0, "fv_tp2d: empty domain %dx%dx%dx%d", ni, nj, nk, nb);
+  B2S_ARGCHECK(0 <= i0 && i0 <= i1 && i1 <= ni && 0 <= j0 && j0 <= j1 && j1 <= nj,
+               "fv_tp2d: rectangle [%d,%d)x[%d,%d) outside the %dx%d domain", i0, i1, j0, j1, ni, nj);
+  B2S_ARGCHECK(q.p && crx.p && xfx.p && cry.p && yfx.p && rarea.p && q_out.p, "fv_tp2d: null field");
+  if (i0 == i1 || j0 == j1) return B2S_OK;
+  const int variant = option("fv_variant", 0);
+  if (variant != 1) {
+    bool applicable = false;
+    int rc = fv_tp2d_tma<T>(ni, nj, nk, nb, i0, i1, j0, j1, q, crx, xfx, cry, yfx, rarea, q_out, s, &applicable);
+    if (applicable) return rc;
+    if (variant == 2) return set_error(B2S_EUNSUPPORTED, "fv_tp2d: fv_variant=2 forced but fields do not meet the TMA alignment rules");
+  }
+  return fv_tp2d_direct<T>(ni, nj, nk, nb, i0, i1, j0, j1, q, crx, xfx, cry, yfx, rarea, q_out, s);
+}
+
+template int fv_tp2d<double>(int, int, int, int, int, int, int, int, F3<const double>, F3<const double>,
+                             F3<const double>, F3<const double>, F3<const double>, F2<const double>, F3<double>,
+                             cudaStream_t);
+template int fv_tp2d<float>(int, int, int, int, int, int, int, int, F3<const float>, F3<const float>,
+                            F3<const float>, F3<const float>, F3<const float>, F2<const float>, F3<float>,
+                            cudaStream_t);
+
+}  // namespace impl
+}  // namespace b2s

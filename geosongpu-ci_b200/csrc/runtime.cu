@@ -1,0 +1,107 @@
+// Runtime half of the C-ABI: init/finalize, thread-local error channel, options, launch counter.
+// Replaces nothing arithmetic in the reference; it is the error channel and lifecycle the
+// reference's void bridge lacks (SURVEY.md 8b "Return / errors", "Lifecycle").
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+
+#include "../../include/b200stencil.h"
+#include "common.cuh"
+
+namespace b2s {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+static int g_device = -1;  // device bound by b2s_init (-1 = not initialised)
+static int g_sms = 0;
+static std::mutex g_mu;
+static std::map<std::string, int> g_options = {
+    {"fv_variant", 0},      // 0 auto, 1 direct (L1/L2) kernel, 2 TMA-pipelined kernel
+    {"column_unroll", 0},   // 0 auto
+};
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(static_cast<int>(e), "%s: %s", what, cudaGetErrorString(e));
+  return B2S_OK;
+}
+
+int sm_count() {
+  if (g_sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+    g_sms = n;
+  }
+  return g_sms;
+}
+
+int option(const char* name, int fallback) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_options.find(name);
+  return it == g_options.end() ? fallback : it->second;
+}
+
+}  // namespace b2s
+
+using namespace b2s;
+
+extern "C" int b2s_init(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return set_error(e == cudaSuccess ? B2S_ENOTINIT : static_cast<int>(e),
+                     "b2s_init: no CUDA device (%s); libb200stencil has no CPU fallback",
+                     e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= n) return set_error(B2S_EINVAL, "b2s_init: device %d out of range [0,%d)", device, n);
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return set_error(static_cast<int>(e), "cudaSetDevice: %s", cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return set_error(static_cast<int>(e), "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10)
+    return set_error(B2S_EUNSUPPORTED, "b2s_init: device is sm_%d%d; this library only ships sm_100a code", prop.major,
+                     prop.minor);
+  g_device = device;
+  g_sms = prop.multiProcessorCount;
+  return B2S_OK;
+}
+
+extern "C" int b2s_finalize(void) {
+  g_device = -1;
+  return B2S_OK;
+}
+
+extern "C" const char* b2s_last_error(void) { return g_err; }
+extern "C" int b2s_device(void) { return g_device; }
+extern "C" int b2s_abi_version(void) { return B2S_ABI_VERSION; }
+extern "C" int b2s_sm_count(void) { return sm_count(); }
+extern "C" int64_t b2s_launch_count(void) { return g_launches.load(); }
+
+extern "C" int b2s_set_option(const char* name, int value) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_options.find(name ? name : "");
+  if (it == g_options.end()) return -1;
+  it->second = value;
+  return 0;
+}
+
+extern "C" int b2s_get_option(const char* name) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_options.find(name ? name : "");
+  return it == g_options.end() ? -1 : it->second;
+}

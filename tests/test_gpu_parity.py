@@ -1,0 +1,288 @@
+"""-m gpu parity tests: every CUDA stencil, called through the C-ABI, against the oracle on the
+same seeded inputs.  Bit-exact for integer / index outputs and pure-move stencils, 1e-12 (fp64) /
+1e-5 (fp32) relative for floating-point fields (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import inputs as gen
+from oracle import numpy_oracle as orc
+from oracle.c_oracle import COracle
+
+pytestmark = pytest.mark.gpu
+
+from gpu_util import assert_close, down, up, up_batch, zeros_like_np  # noqa: E402
+
+RTOL = {np.float64: 1e-12, np.float32: 1e-5}
+DTYPES = [np.float64, np.float32]
+# (ni, nj, nk): golden size, cfg1 size, ragged sizes (scalar path), vector-friendly, tall
+SHAPES = [(3, 3, 4), (24, 24, 72), (17, 5, 9), (1, 1, 1), (33, 2, 137), (96, 96, 72), (64, 3, 5)]
+
+
+@pytest.fixture(scope="module")
+def st():
+    from b200stencil import stencils
+
+    return stencils
+
+
+@pytest.fixture(scope="module")
+def corc():
+    return COracle()
+
+
+def tdt(dtype):
+    return torch.float64 if dtype == np.float64 else torch.float32
+
+
+def idt(dtype):
+    return np.int64 if dtype == np.float64 else np.int32
+
+
+# ---- the reference's own golden vectors, on the GPU ------------------------------------------------
+
+
+def test_golden_top_of_column(st):
+    I = up(gen.golden_column_input())
+    O = up(np.zeros((3, 3, 4)))
+    tmp = up(np.zeros((3, 3)))
+    st.top_of_column(I, tmp, O)
+    assert np.all(down(O) == 42) and np.all(down(tmp) == 42)
+
+
+def test_golden_while_in_function(st):
+    I = up(gen.golden_column_input())
+    O = up(np.zeros((3, 3, 4)))
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    st.while_in_function(I, O, undefined_count=cnt)
+    assert (down(O)[0, 0, :] == [3.0, 2.0, 1.0, 0.0]).all()
+    assert int(cnt.item()) == 0
+
+
+# ---- S1-S3 ------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("align", [True, False])
+def test_patterns(st, shape, dtype, align):
+    ni, nj, nk = shape
+    P = gen.top_of_column_inputs(ni, nj, nk, dtype)
+    o, t = zeros_like_np(shape, dtype), zeros_like_np(shape[:2], dtype)
+    orc.top_of_column(P, t, o)
+    dO, dT = up(np.zeros(shape, dtype), align), up(np.zeros(shape[:2], dtype), align)
+    st.top_of_column(up(P, align), dT, dO)
+    assert np.array_equal(down(dO), o) and np.array_equal(down(dT), t)
+
+    W = gen.while_inputs(ni, nj, nk, dtype)
+    o = zeros_like_np(shape, dtype)
+    assert orc.while_in_function_scan(W, o) == 0
+    dO = up(np.zeros(shape, dtype), align)
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    st.while_in_function(up(W, align), dO, undefined_count=cnt)
+    assert np.array_equal(down(dO), o) and int(cnt.item()) == 0
+
+    for miss in (0.0, 0.3):
+        data, kmask, kidx = gen.hybrid_inputs(ni, nj, nk, dtype, miss_fraction=miss)
+        o = zeros_like_np(shape[:2], dtype)
+        orc.hybrid_index_2dout(data, kmask, kidx, o)
+        dO = up(np.zeros(shape[:2], dtype), align)
+        st.hybrid_index_2dout(up(data, align), up(kmask, align), up(kidx, align), dO)
+        assert np.array_equal(down(dO), o)
+
+
+def test_while_literal_form_matches(st):
+    """The literal per-point while (not the scan restatement) is what the GPU must reproduce."""
+    ni, nj, nk = 12, 7, 19
+    W = gen.while_inputs(ni, nj, nk)
+    o = zeros_like_np((ni, nj, nk), np.float64)
+    orc.while_in_function(W, o)
+    dO = up(np.zeros((ni, nj, nk)))
+    st.while_in_function(up(W), dO)
+    assert np.array_equal(down(dO), o)
+
+
+def test_while_undefined_is_counted(st):
+    I = np.ones((4, 2, 5))
+    I[0, 0, 4] = 7.0  # one defined column
+    O = up(np.zeros_like(I))
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    st.while_in_function(up(I), O, undefined_count=cnt)
+    ref = np.zeros_like(I)
+    n = orc.while_in_function_scan(I, ref)
+    assert int(cnt.item()) == n == 7 * 5
+    assert np.array_equal(down(O), ref)
+    st.while_in_function(up(I), O)  # NULL counter is allowed
+
+
+def test_hybrid_arbitrary_mask_last_match_wins(st):
+    data, kmask, kidx = gen.hybrid_inputs(8, 6, 10)
+    rng = np.random.default_rng(5)
+    kmask = gen.as_ifirst(rng.integers(0, 4, size=kmask.shape).astype(np.float64))
+    kidx = gen.as_ifirst(rng.integers(0, 5, size=kidx.shape).astype(np.float64))
+    o = zeros_like_np((8, 6), np.float64)
+    o[...] = -5.0  # prior contents survive where nothing matches
+    dO = up(o.copy())
+    orc.hybrid_index_2dout(data, kmask, kidx, o)
+    st.hybrid_index_2dout(up(data), up(kmask), up(kidx), dO)
+    assert np.array_equal(down(dO), o)
+    assert (o == -5.0).any()
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_patterns_batched_tiles(st, dtype):
+    """6 tiles in one launch (cfg2 shape class), including halo-padded storage via slicing."""
+    ni, nj, nk, nb = 12, 10, 9, 6
+    Ws = [gen.while_inputs(ni, nj, nk, dtype, cfg=20 + b) for b in range(nb)]
+    dW = up_batch(Ws)
+    big = torch.zeros((nb, ni + 6, nj + 6, nk), dtype=tdt(dtype), device="cuda").permute(0, 1, 2, 3)
+    store = torch.zeros((nb, nk, nj + 6, ni + 6), dtype=tdt(dtype), device="cuda")
+    dO = store.permute(0, 3, 2, 1)[:, 3:-3, 3:-3, :]  # compute window of a halo-3 field
+    st.while_in_function(dW, dO)
+    for b in range(nb):
+        o = zeros_like_np((ni, nj, nk), dtype)
+        orc.while_in_function_scan(Ws[b], o)
+        assert np.array_equal(down(dO[b]), o)
+    assert float(store.sum()) == float(dO.sum())  # halo cells untouched (writes stay in the domain)
+    del big
+
+
+# ---- S4 ------------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("shape", [(3, 3, 4), (24, 24, 72), (7, 11, 13), (64, 8, 72)])
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_moist(st, shape, dtype):
+    ni, nj, nk = shape
+    m = gen.moist_inputs(ni, nj, nk, dtype)
+    k1, p1 = zeros_like_np(shape[:2], idt(dtype)), zeros_like_np(shape[:2], dtype)
+    p1[...] = -1.0
+    dK = up(np.zeros(shape[:2], idt(dtype)))
+    dP = up(p1.copy())
+    orc.find_klcl(m["p"], m["PLCL"], k1, p1)
+    st.find_klcl(up(m["p"]), up(m["PLCL"]), dK, dP)
+    assert np.array_equal(down(dK), k1) and np.array_equal(down(dP), p1)
+    # nothing found: KLCL = -1, PLmb_at_KLCL untouched
+    hi = np.full(shape[:2], 1.0, dtype)
+    st.find_klcl(up(m["p"]), up(hi), dK, dP)
+    assert np.all(down(dK) == -1) and np.array_equal(down(dP), p1)
+
+    c1 = zeros_like_np(shape[:2], idt(dtype))
+    dC = up(np.zeros(shape[:2], idt(dtype)))
+    orc.cloud_top(m["ql"], c1)
+    st.cloud_top(up(m["ql"]), dC)
+    assert np.array_equal(down(dC), c1)
+    st.cloud_top(up(np.zeros(shape, dtype)), dC)
+    assert np.all(down(dC) == -1)
+
+    a = {k: gen.as_ifirst(m[k]) for k in ("T", "q", "ql")}
+    d = {k: up(m[k]) for k in ("T", "q", "ql")}
+    orc.saturation_adjust(a["T"], a["q"], a["ql"], m["p"])
+    st.saturation_adjust(d["T"], d["q"], d["ql"], up(m["p"]))
+    for k in a:
+        assert_close(down(d[k]), a[k], RTOL[dtype], k)
+
+
+# ---- S5 ------------------------------------------------------------------------------------------------
+
+
+def _fv_case(st, corc, ni, nj, nk, dtype, variant=0, region=None, align=True):
+    from b200stencil import _abi
+
+    f = gen.fv_inputs(ni, nj, nk, dtype)
+    ref = zeros_like_np((ni, nj, nk), dtype)
+    corc.fv_tp2d(f["q"], f["crx"], f["xfx"], f["cry"], f["yfx"], f["rarea"], ref)
+    d = {k: up(v, align) for k, v in f.items()}
+    out = up(np.full((ni, nj, nk), -7.0, dtype), align)
+    _abi.set_option("fv_variant", variant)
+    try:
+        st.fv_tp2d(d["q"], d["crx"], d["xfx"], d["cry"], d["yfx"], d["rarea"], out, region=region)
+    finally:
+        _abi.set_option("fv_variant", 0)
+    got = down(out)
+    if region is None:
+        assert_close(got, ref, RTOL[dtype], "q_out")
+    else:
+        i0, i1, j0, j1 = region
+        assert_close(got[i0:i1, j0:j1], ref[i0:i1, j0:j1], RTOL[dtype], "q_out[region]")
+        mask = np.ones((ni, nj), bool)
+        mask[i0:i1, j0:j1] = False
+        assert np.all(got[mask] == -7.0)  # nothing written outside the rectangle
+
+
+@pytest.mark.parametrize("shape", [(3, 3, 4), (24, 24, 8), (13, 7, 5), (1, 1, 2), (130, 20, 3), (128, 64, 2), (300, 9, 2)])
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("variant", [0, 1])
+def test_fv_tp2d(st, corc, shape, dtype, variant):
+    _fv_case(st, corc, *shape, dtype, variant=variant)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_fv_tp2d_regions_and_unaligned(st, corc, variant):
+    _fv_case(st, corc, 40, 30, 3, np.float64, variant, region=(3, 37, 3, 27))
+    _fv_case(st, corc, 40, 30, 3, np.float64, variant, region=(0, 40, 0, 3))
+    _fv_case(st, corc, 40, 30, 3, np.float64, variant, region=(37, 40, 3, 27))
+    _fv_case(st, corc, 40, 30, 3, np.float32, variant, region=(5, 5, 0, 30))  # empty
+    _fv_case(st, corc, 37, 11, 3, np.float64, variant, align=False)  # odd strides: general path
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_fv_tp2d_batched(st, corc, dtype):
+    ni, nj, nk, nb = 20, 12, 4, 3
+    fs = [gen.fv_inputs(ni, nj, nk, dtype, cfg=40 + b) for b in range(nb)]
+    d = {k: up_batch([f[k] for f in fs]) for k in fs[0]}
+    out = up_batch([np.zeros((ni, nj, nk), dtype)] * nb)
+    st.fv_tp2d(d["q"], d["crx"], d["xfx"], d["cry"], d["yfx"], d["rarea"], out)
+    for b in range(nb):
+        ref = zeros_like_np((ni, nj, nk), dtype)
+        f = fs[b]
+        corc.fv_tp2d(f["q"], f["crx"], f["xfx"], f["cry"], f["yfx"], f["rarea"], ref)
+        assert_close(down(out[b]), ref, RTOL[dtype], f"q_out[{b}]")
+
+
+# ---- S6 ------------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("shape", [(3, 3, 4), (12, 9, 72), (5, 4, 137), (64, 40, 20)])
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_vertical(st, shape, dtype):
+    ni, nj, nk = shape
+    nk2 = nk + 3 if nk > 4 else nk
+    v = gen.vertical_inputs(ni, nj, nk, dtype, nk2=nk2)
+    pe = up(np.zeros((ni, nj, nk + 1), dtype))
+    st.pe_prefix(up(v["delp"]), v["ptop"], pe)
+    assert np.array_equal(down(pe), v["pe1"])  # sequential-in-k adds, no contraction: bit-exact
+
+    ref = zeros_like_np((ni, nj, nk2), dtype)
+    orc.remap(v["pe1"], v["q1"], v["pe2"], ref)
+    q2 = up(np.zeros((ni, nj, nk2), dtype))
+    st.remap(up(v["pe1"]), up(v["q1"]), up(v["pe2"]), q2)
+    assert_close(down(q2), ref, RTOL[dtype], "q2")
+    assert np.array_equal(down(q2), ref), "remap is compiled without FMA contraction: expected bit-exact"
+
+    t = gen.tridiag_inputs(ni, nj, nk, dtype)
+    ref = zeros_like_np(shape, dtype)
+    orc.tridiag(t["a"], t["b"], t["c"], t["d"], ref)
+    x = up(np.zeros(shape, dtype))
+    st.tridiag(up(t["a"]), up(t["b"]), up(t["c"]), up(t["d"]), x)
+    assert_close(down(x), ref, RTOL[dtype], "x")
+
+
+# ---- error channel ---------------------------------------------------------------------------------------
+
+
+def test_error_channel(st):
+    from b200stencil import _abi
+
+    I = up(np.zeros((4, 4, 4)))
+    with pytest.raises(TypeError):
+        st.top_of_column(I.cpu(), up(np.zeros((4, 4))), I)  # host tensor: no CPU path
+    with pytest.raises(TypeError):
+        st.top_of_column(I, up(np.zeros((4, 4), np.float32)), I)  # dtype mismatch: no casting
+    q = up(np.zeros((10, 10, 2)))
+    with pytest.raises(_abi.B200StencilError) as e:
+        st.fv_tp2d(q, q, q, q, q, up(np.zeros((4, 4))), up(np.zeros((4, 4, 2))), region=(0, 9, 0, 4))
+    assert "rectangle" in str(e.value)
+    bad = torch.zeros((4, 4, 4), dtype=torch.float64, device="cuda")  # k-fastest: rejected
+    with pytest.raises(ValueError):
+        st.top_of_column(bad, up(np.zeros((4, 4))), I)
