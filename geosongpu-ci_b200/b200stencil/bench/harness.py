@@ -116,6 +116,37 @@ def time_kernel(fn: Callable[[int], None], iters: int = 20, warmup: int = 3, flu
     return {"min_ms": min(ms), "median_ms": statistics.median(ms), "mean_ms": sum(ms) / len(ms), "iters": iters}
 
 
+def time_graph(fn: Callable[[int], None], rotate: int = 1, launches_per_graph: int = 20, iters: int = 10,
+               warmup: int = 3) -> Dict[str, float]:
+    """Per-launch device time with launch overhead removed: ``launches_per_graph`` calls of
+    ``fn(slot)`` (slots rotating, so the working set exceeds L2) are captured into one CUDA graph and
+    the replays are timed with CUDA events.  For kernels of a few microseconds, where the host
+    cannot issue launches as fast as the device retires them."""
+    stream = torch.cuda.Stream()
+    stream.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(stream):
+        for it in range(max(warmup, rotate)):
+            fn(it % rotate)
+    stream.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=stream):
+        for it in range(launches_per_graph):
+            fn(it % rotate)
+    for _ in range(warmup):
+        graph.replay()
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        graph.replay()
+        b.record()
+        b.synchronize()
+        ms.append(a.elapsed_time(b) / launches_per_graph)
+    return {"min_ms": min(ms), "median_ms": statistics.median(ms), "mean_ms": sum(ms) / len(ms), "iters": iters,
+            "launches_per_graph": launches_per_graph}
+
+
 def roofline(bytes_per_launch: float, ms: float, peak_gbs: float) -> Dict[str, float]:
     achieved = bytes_per_launch / (ms * 1e-3) / 1e9
     return {"achieved": achieved, "peak": peak_gbs, "frac": achieved / peak_gbs, "frac_of_nominal_8TBs": achieved / NOMINAL_HBM_GBS}

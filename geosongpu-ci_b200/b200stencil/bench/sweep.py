@@ -10,14 +10,17 @@ import torch
 from . import harness, workloads
 
 
-def run_one(stencil: str, config: str, dtype, iters: int, warmup: int) -> dict:
+def run_one(stencil: str, config: str, dtype, iters: int, warmup: int, graph: bool = False) -> dict:
     tiles, n, nk = workloads.CONFIGS[config]
     wl = workloads.make(stencil, tiles, n, nk, dtype)
-    t = harness.time_kernel(wl.run, iters=iters, warmup=warmup, rotate=wl.slots)
+    if graph:
+        t = harness.time_graph(wl.run, rotate=wl.slots, launches_per_graph=max(wl.slots * 4, 16), iters=iters, warmup=warmup)
+    else:
+        t = harness.time_kernel(wl.run, iters=iters, warmup=warmup, rotate=wl.slots)
     peaks = harness.measured_peaks()
     rf = harness.roofline(wl.bytes_per_launch, t["median_ms"], peaks["hbm_gbs"])
     out = {
-        "stencil": stencil, "config": config, "dtype": "f64" if dtype == torch.float64 else "f32",
+        "stencil": stencil, "config": config, "timing": "cuda-graph replay" if graph else "events per launch", "dtype": "f64" if dtype == torch.float64 else "f32",
         "points": wl.points, "bytes_per_point": round(wl.bytes_per_point, 3), "slots": wl.slots,
         "median_ms": round(t["median_ms"], 4), "min_ms": round(t["min_ms"], 4),
         "gpts_per_s": round(wl.points / (t["median_ms"] * 1e-3) / 1e9, 3),
@@ -39,13 +42,22 @@ def main(argv=None) -> int:
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--graph", action="store_true", help="time CUDA-graph replays (removes host launch overhead)")
+    ap.add_argument("--option", action="append", default=[], help="libb200stencil option name=value")
     ns = ap.parse_args(argv)
+    from .. import _abi
+
+    for opt in ns.option:
+        name, value = opt.split("=")
+        _abi.set_option(name, int(value))
     rows = []
     for stencil in ns.stencils.split(","):
         for d in ns.dtypes.split(","):
             dtype = torch.float64 if d == "f64" else torch.float32
             cfg = ns.config or workloads.DEFAULT_CONFIG[stencil]
-            row = run_one(stencil, cfg, dtype, ns.iters, ns.warmup)
+            row = run_one(stencil, cfg, dtype, ns.iters, ns.warmup, ns.graph)
+            if ns.option:
+                row["options"] = ns.option
             rows.append(row)
             print(json.dumps(row), flush=True)
     if ns.out:

@@ -88,10 +88,10 @@ def make(stencil: str, tiles: int, n: int, nk: int, dtype=torch.float64, seed: i
         ns = slots or _slots_for(pts * bpp)
         sets = []
         for _ in range(ns):
-            data = torch.floor(_rand(shp3, dtype, tiles, 800, 900, g))
+            data = _rand(shp3, dtype, tiles, 800, 900, g).floor_()
             kmask = fields.empty(shp3, dtype, batch=tiles)
             kmask[...] = torch.arange(nk, device="cuda", dtype=dtype)
-            kidx = torch.floor(_rand(shp2, dtype, tiles, 0, nk, g)).clamp_(0, nk - 1)
+            kidx = _rand(shp2, dtype, tiles, 0, nk, g).floor_().clamp_(0, nk - 1)
             sets.append((data, kmask, kidx, fields.zeros(shp2, dtype, batch=tiles)))
         return Workload(name, stencil, pts, bpp, lambda s: stencils.hybrid_index_2dout(*sets[s]), ns, keep=sets,
                         notes="algorithmic bytes count data_field in full (SURVEY 8d); the kernel only touches the sectors holding a match")
@@ -132,7 +132,7 @@ def make(stencil: str, tiles: int, n: int, nk: int, dtype=torch.float64, seed: i
             T += (210.0 + 90.0 * k / nk).to(dtype)
             es_ = 611.2 * torch.exp(17.67 * (T - 273.15) / (T - 29.65))
             qs = 0.622 * es_ / (p - 0.378 * es_)
-            q = _rand(shp3, dtype, tiles, 0, 1.2, g) * qs
+            q = _rand(shp3, dtype, tiles, 0, 1.2, g).mul_(qs)
             ql = fields.empty(shp3, dtype, batch=tiles)
             ql.normal_(0.0, 1e-4, generator=g).clamp_(min=0.0)
             sets.append((T, q, ql, p))
@@ -147,8 +147,8 @@ def make(stencil: str, tiles: int, n: int, nk: int, dtype=torch.float64, seed: i
             q = _rand((ni + 6, nj + 6, nk), dtype, tiles, 0.5, 1.5, g)
             crx = _rand((ni + 1, nj, nk), dtype, tiles, -0.9, 0.9, g)
             cry = _rand((ni, nj + 1, nk), dtype, tiles, -0.9, 0.9, g)
-            xfx = crx * _rand((ni + 1, nj, nk), dtype, tiles, 0.9, 1.1, g)
-            yfx = cry * _rand((ni, nj + 1, nk), dtype, tiles, 0.9, 1.1, g)
+            xfx = _rand((ni + 1, nj, nk), dtype, tiles, 0.9, 1.1, g).mul_(crx)  # in place: keeps the padded rows
+            yfx = _rand((ni, nj + 1, nk), dtype, tiles, 0.9, 1.1, g).mul_(cry)
             rarea = _rand(shp2, dtype, tiles, 0.9, 1.1, g)
             sets.append((q, crx, xfx, cry, yfx, rarea, fields.empty(shp3, dtype, batch=tiles)))
         return Workload(name, stencil, pts, bpp, lambda s: stencils.fv_tp2d(*sets[s]), ns, keep=sets)
@@ -179,8 +179,8 @@ def make(stencil: str, tiles: int, n: int, nk: int, dtype=torch.float64, seed: i
         ns = slots or _slots_for(pts * bpp, cap=3)
         sets = []
         for _ in range(ns):
-            a = -_rand(shp3, dtype, tiles, 0, 1, g)
-            c = -_rand(shp3, dtype, tiles, 0, 1, g)
+            a = _rand(shp3, dtype, tiles, 0, 1, g).neg_()
+            c = _rand(shp3, dtype, tiles, 0, 1, g).neg_()
             b = _rand(shp3, dtype, tiles, 2, 3, g)
             d = _rand(shp3, dtype, tiles, -1, 1, g)
             sets.append((a, b, c, d, fields.empty(shp3, dtype, batch=tiles), fields.empty(shp3, dtype, batch=tiles)))

@@ -1,14 +1,460 @@
-// K5 (variant 2, TMA-pipelined) -- placeholder until the kernel lands: reports "not applicable".
+// K5 (variant 2, TMA-pipelined): fv_tp2d as a persistent, warp-specialised sm_100a kernel.
+// Spec: oracle/numpy_oracle.py fv_tp2d (no source in /root/reference).
+//
+// Design (DESIGN.md "K5"):
+//   * work item = one TI x R tile of one (k, b) level; a persistent grid (CTAs/SM x 148 SMs)
+//     walks the item list round-robin, so there is no tail wave and no per-tile launch cost;
+//   * warp 4 is the PRODUCER: one elected lane issues five 4-D TMA tile loads per item
+//     (cp.async.bulk.tensor.4d -> SASS UTMALDG): q with its 3-cell apron ((TI+6) x (R+6)),
+//     crx/xfx ((TI+1) x R) and cry/yfx (TI x (R+1)), completing on an mbarrier (expect_tx);
+//   * warps 0-3 are CONSUMERS: thread = one i-column of the tile, marching the R rows with the
+//     y-direction window (7 q values, 3 interface values, the low-side flux) carried in
+//     registers; x-direction neighbours come from the shared-memory tile (conflict-free:
+//     consecutive lanes read consecutive elements).  Results go straight to HBM (coalesced,
+//     streaming stores);
+//   * NSTAGE-deep full/empty mbarrier ring: loads of the next items are in flight while the
+//     current one is computed, independent of occupancy;
+//   * every input element crosses HBM once; apron re-reads (q: (R+6)/R, cry/yfx: (R+1)/R) are
+//     L2 hits because neighbouring tiles are consecutive in the item order.
+// Algorithmic bytes/point: 40 R + 8 W + 8/nk (same as variant 1).
+#include <cuda.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "fv_math.cuh"
 #include "impl.cuh"
 
 namespace b2s {
 namespace impl {
 
+namespace {
+
+// ---- PTX wrappers (mbarrier + TMA) ------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+constexpr int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// ---- compile-time tile geometry -------------------------------------------------------------------
+
+template <typename T, int TI, int R, int NSTAGE>
+struct Tile {
+  static constexpr int V = 16 / sizeof(T);          // elements per 16 B
+  // A TMA box must START on a 16-byte boundary of global memory (an odd fp64 start coordinate
+  // faults with "illegal instruction"), so every box begins at the aligned column at or before
+  // the one needed and is V-1 elements wider; the consumer skips `shift` leading elements.
+  static constexpr int BQ = round_up(TI + 6 + V - 1, V);  // q box: columns i_s-3 .. i_s+TI+2
+  static constexpr int BX = round_up(TI + 1 + V - 1, V);  // crx/xfx box: interfaces i_s .. i_s+TI
+  static constexpr int BY = round_up(TI + V - 1, V);      // cry/yfx box
+  static constexpr int RQ = R + 6, RX = R, RY = R + 1;
+  static constexpr int Q_BYTES = RQ * BQ * sizeof(T);
+  static constexpr int X_BYTES = RX * BX * sizeof(T);
+  static constexpr int Y_BYTES = RY * BY * sizeof(T);
+  static constexpr int Q_OFF = 0;
+  static constexpr int CRX_OFF = round_up(Q_BYTES, 128);
+  static constexpr int XFX_OFF = CRX_OFF + round_up(X_BYTES, 128);
+  static constexpr int CRY_OFF = XFX_OFF + round_up(X_BYTES, 128);
+  static constexpr int YFX_OFF = CRY_OFF + round_up(Y_BYTES, 128);
+  static constexpr int STAGE_BYTES = YFX_OFF + round_up(Y_BYTES, 128);
+  static constexpr int TX_BYTES = Q_BYTES + 2 * X_BYTES + 2 * Y_BYTES;
+  static constexpr int BAR_OFF = NSTAGE * STAGE_BYTES;
+  static constexpr int SMEM_BYTES = BAR_OFF + 2 * NSTAGE * 8;
+  static constexpr int THREADS = TI + 32;
+  static_assert(BQ <= 256 && BX <= 256 && RQ <= 256, "TMA box dimensions are limited to 256 elements");
+};
+
 template <typename T>
-int fv_tp2d_tma(int, int, int, int, int, int, int, int, F3<const T>, F3<const T>, F3<const T>, F3<const T>,
-                F3<const T>, F2<const T>, F3<T>, cudaStream_t, bool* applicable) {
+struct FvTmaParams {
+  int nk, nb, i0, i1, j0, j1;
+  int nstrips, njblk;
+  int nitems;
+  // per field: c = TMA coordinate of compute column i0 (tensor base is 16-byte aligned), sh = c % V.
+  // The box of a tile starts at c - sh + strip*TI; the tile's first needed element sits sh further.
+  int c_q, c_crx, c_xfx, c_cry, c_yfx;
+  int sh_q, sh_crx, sh_xfx, sh_cry, sh_yfx;
+  F2<const T> rarea;
+  F3<T> qout;
+};
+
+// Position of a work item, advanced by gridDim.x items per step without divisions:
+// item -> (jb fastest, strip, k, b).
+struct ItemCursor {
+  int jb, strip, k, b;
+  int d_jb, d_strip, d_k, d_b;
+  __device__ __forceinline__ void init(int item, int step, int njblk, int nstrips, int nk) {
+    jb = item % njblk;
+    int t = item / njblk;
+    strip = t % nstrips;
+    t /= nstrips;
+    k = t % nk;
+    b = t / nk;
+    d_jb = step % njblk;
+    t = step / njblk;
+    d_strip = t % nstrips;
+    t /= nstrips;
+    d_k = t % nk;
+    d_b = t / nk;
+  }
+  __device__ __forceinline__ void advance(int njblk, int nstrips, int nk) {
+    jb += d_jb;
+    if (jb >= njblk) {
+      jb -= njblk;
+      strip += 1;
+    }
+    strip += d_strip;
+    if (strip >= nstrips) {
+      strip -= nstrips;
+      k += 1;
+    }
+    k += d_k;
+    if (k >= nk) {
+      k -= nk;
+      b += 1;
+    }
+    b += d_b;
+  }
+};
+
+template <typename T, int TI, int R, int NSTAGE>
+__global__ void __launch_bounds__(TI + 32) k_fv_tma(const __grid_constant__ CUtensorMap tm_q,
+                                                    const __grid_constant__ CUtensorMap tm_crx,
+                                                    const __grid_constant__ CUtensorMap tm_xfx,
+                                                    const __grid_constant__ CUtensorMap tm_cry,
+                                                    const __grid_constant__ CUtensorMap tm_yfx,
+                                                    const FvTmaParams<T> P) {
+  using G = Tile<T, TI, R, NSTAGE>;
+  // Indexed straight off the __shared__ symbol so the compiler keeps the address space (LDS with
+  // immediate offsets, not generic LD).  TMA needs 128-byte aligned destinations: the dynamic
+  // shared window of a CTA without static shared memory starts 1024-byte aligned.
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + G::BAR_OFF);
+  uint64_t* empty = full + NSTAGE;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr int NCONS_WARPS = TI / 32;
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 127u) __trap();
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(&full[s], 1);             // producer's arrive.expect_tx
+      mbar_init(&empty[s], NCONS_WARPS);  // one arrive per consumer warp
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  ItemCursor cur;
+  cur.init(blockIdx.x, gridDim.x, P.njblk, P.nstrips, P.nk);
+  const int nmine = (P.nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == NCONS_WARPS) {
+    // =============================== PRODUCER ===============================
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_q);
+      tma_prefetch_desc(&tm_crx);
+      tma_prefetch_desc(&tm_xfx);
+      tma_prefetch_desc(&tm_cry);
+      tma_prefetch_desc(&tm_yfx);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int n = 0; n < nmine; ++n) {
+        const int io = cur.strip * TI;     // column offset of the tile inside the rectangle
+        const int js = P.j0 + cur.jb * R;  // first compute row of the tile
+        mbar_wait(&empty[stage], phase ^ 1);
+        unsigned char* st = smem + stage * G::STAGE_BYTES;
+        mbar_arrive_expect_tx(&full[stage], G::TX_BYTES);
+        // q's tensor map is based at the halo origin (-3,-3): compute cell i-3 is coordinate i, row j-3 is row j
+        tma_load_4d(st + G::Q_OFF, &tm_q, &full[stage], P.c_q - P.sh_q + io, js, cur.k, cur.b);
+        tma_load_4d(st + G::CRX_OFF, &tm_crx, &full[stage], P.c_crx - P.sh_crx + io, js, cur.k, cur.b);
+        tma_load_4d(st + G::XFX_OFF, &tm_xfx, &full[stage], P.c_xfx - P.sh_xfx + io, js, cur.k, cur.b);
+        tma_load_4d(st + G::CRY_OFF, &tm_cry, &full[stage], P.c_cry - P.sh_cry + io, js, cur.k, cur.b);
+        tma_load_4d(st + G::YFX_OFF, &tm_yfx, &full[stage], P.c_yfx - P.sh_yfx + io, js, cur.k, cur.b);
+        cur.advance(P.njblk, P.nstrips, P.nk);
+        if (++stage == NSTAGE) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+    return;
+  }
+
+  // =============================== CONSUMERS ===============================
+  const int ci = threadIdx.x;  // column of the tile owned by this thread
+  // per-thread element offsets into a stage (constant for the whole kernel)
+  const int oq = G::Q_OFF / (int)sizeof(T) + ci + P.sh_q;
+  const int ocx = G::CRX_OFF / (int)sizeof(T) + ci + P.sh_crx;
+  const int oxf = G::XFX_OFF / (int)sizeof(T) + ci + P.sh_xfx;
+  const int ocy = G::CRY_OFF / (int)sizeof(T) + ci + P.sh_cry;
+  const int oyf = G::YFX_OFF / (int)sizeof(T) + ci + P.sh_yfx;
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int n = 0; n < nmine; ++n) {
+    const int i = P.i0 + cur.strip * TI + ci;
+    const int js = P.j0 + cur.jb * R;
+    const int nrows = i < P.i1 ? min(R, P.j1 - js) : 0;  // rows of this tile this thread stores
+    const T* rap = P.rarea.at(i, js, cur.b);
+    T* outp = P.qout.at(i, js, cur.k, cur.b);
+    cur.advance(P.njblk, P.nstrips, P.nk);
+
+    // rarea does not go through shared memory: R independent loads issued before the wait
+    T ra[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) ra[r] = r < nrows ? __ldg(rap + (int64_t)r * P.rarea.sj) : T(0);
+
+    mbar_wait(&full[stage], phase);
+    const T* st = reinterpret_cast<const T*>(smem + stage * G::STAGE_BYTES);
+    const T* qs = st + oq;    // qs[r*BQ + c]: row js-3+r, column i-3+c
+    const T* cxs = st + ocx;  // [r*BX + {0,1}]: interfaces i, i+1
+    const T* xfs = st + oxf;
+    const T* cys = st + ocy;  // [r*BY]: interface js+r
+    const T* yfs = st + oyf;
+
+    // y-direction window centred on row js (q0), carried down the tile
+    T qm2 = qs[1 * G::BQ + 3], qm1 = qs[2 * G::BQ + 3], q0 = qs[3 * G::BQ + 3];
+    T qp1 = qs[4 * G::BQ + 3], qp2 = qs[5 * G::BQ + 3];
+    T al_0 = ppm_al(qm2, qm1, q0, qp1);
+    T al_p1 = ppm_al(qm1, q0, qp1, qp2);
+    T fy_lo;
+    {
+      const T al_m1 = ppm_al(qs[0 * G::BQ + 3], qm2, qm1, q0);
+      fy_lo = ppm_flux_from_al(qm1, q0, al_m1, al_0, al_p1, cys[0]) * yfs[0];
+    }
+
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const T qp3 = qs[(r + 6) * G::BQ + 3];
+      const T al_p2 = ppm_al(q0, qp1, qp2, qp3);
+      const T fy_hi = ppm_flux_from_al(q0, qp1, al_0, al_p1, al_p2, cys[(r + 1) * G::BY]) * yfs[(r + 1) * G::BY];
+      // x direction on row js + r (shared-memory row r + 3)
+      const T* row = qs + (r + 3) * G::BQ;
+      const T xm3 = row[0], xm2 = row[1], xm1 = row[2], xp1 = row[4], xp2 = row[5], xp3 = row[6];
+      const T ax_m1 = ppm_al(xm3, xm2, xm1, q0), ax_0 = ppm_al(xm2, xm1, q0, xp1);
+      const T ax_p1 = ppm_al(xm1, q0, xp1, xp2), ax_p2 = ppm_al(q0, xp1, xp2, xp3);
+      const T fx_lo = ppm_flux_from_al(xm1, q0, ax_m1, ax_0, ax_p1, cxs[r * G::BX]) * xfs[r * G::BX];
+      const T fx_hi = ppm_flux_from_al(q0, xp1, ax_0, ax_p1, ax_p2, cxs[r * G::BX + 1]) * xfs[r * G::BX + 1];
+      if (r < nrows) __stcs(outp + (int64_t)r * P.qout.sj, q0 - ra[r] * ((fx_hi - fx_lo) + (fy_hi - fy_lo)));
+      // slide the window one row down
+      qm1 = q0;
+      q0 = qp1;
+      qp1 = qp2;
+      qp2 = qp3;
+      al_0 = al_p1;
+      al_p1 = al_p2;
+      fy_lo = fy_hi;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[stage]);
+    if (++stage == NSTAGE) {
+      stage = 0;
+      phase ^= 1;
+    }
+  }
+}
+
+// ---- host side: tensor maps ---------------------------------------------------------------------
+
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn encode_fn() {
+  static EncodeFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeFn>(p);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* base;
+  int64_t sj, sk, sb;
+  int e0, e1, e2, e3, b0, b1, es;
+  bool operator<(const MapKey& o) const {
+    return std::tie(base, sj, sk, sb, e0, e1, e2, e3, b0, b1, es) <
+           std::tie(o.base, o.sj, o.sk, o.sb, o.e0, o.e1, o.e2, o.e3, o.b0, o.b1, o.es);
+  }
+};
+std::map<MapKey, CUtensorMap> g_maps;
+std::mutex g_maps_mu;
+
+// A field as TMA sees it: 16-byte aligned base `p - off` (off elements), extents in elements.
+template <typename T>
+struct TmaField {
+  const T* base;
+  int off;
+  bool ok;
+};
+
+template <typename T>
+TmaField<T> tma_field(const T* first, int64_t sj, int64_t sk, int64_t sb, int nk, int nb) {
+  constexpr int V = 16 / sizeof(T);
+  TmaField<T> f;
+  const uintptr_t a = reinterpret_cast<uintptr_t>(first);
+  f.off = static_cast<int>((a % 16) / sizeof(T));
+  f.base = first - f.off;
+  f.ok = (a % sizeof(T) == 0) && sj > 0 && sj % V == 0 && (nk == 1 || (sk > 0 && sk % V == 0)) &&
+         (nb == 1 || (sb > 0 && sb % V == 0));
+  return f;
+}
+
+template <typename T>
+bool make_map(CUtensorMap* out, const T* base, int64_t sj, int64_t sk, int64_t sb, int e0, int e1, int e2, int e3,
+              int b0, int b1) {
+  MapKey key{base, sj, sk, sb, e0, e1, e2, e3, b0, b1, (int)sizeof(T)};
+  {
+    std::lock_guard<std::mutex> lk(g_maps_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) {
+      *out = it->second;
+      return true;
+    }
+  }
+  EncodeFn enc = encode_fn();
+  if (!enc) return false;
+  // size-1 axes still need a legal (multiple-of-16, non-zero) stride
+  const int64_t sk_b = (e2 > 1 ? sk : sj * e1) * (int64_t)sizeof(T);
+  const int64_t sb_b = (e3 > 1 ? sb : (e2 > 1 ? sk * e2 : sj * e1)) * (int64_t)sizeof(T);
+  cuuint64_t dims[4] = {(cuuint64_t)e0, (cuuint64_t)e1, (cuuint64_t)e2, (cuuint64_t)e3};
+  cuuint64_t strides[3] = {(cuuint64_t)(sj * sizeof(T)), (cuuint64_t)sk_b, (cuuint64_t)sb_b};
+  cuuint32_t box[4] = {(cuuint32_t)b0, (cuuint32_t)b1, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUtensorMapDataType dt = sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUresult r = enc(out, dt, 4, const_cast<T*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return false;
+  std::lock_guard<std::mutex> lk(g_maps_mu);
+  if (g_maps.size() > 256) g_maps.clear();
+  g_maps[key] = *out;
+  return true;
+}
+
+template <typename T, int TI, int R, int NSTAGE>
+int launch(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j1, F3<const T> q, F3<const T> crx,
+           F3<const T> xfx, F3<const T> cry, F3<const T> yfx, F2<const T> rarea, F3<T> q_out, cudaStream_t s,
+           bool* applicable) {
+  using G = Tile<T, TI, R, NSTAGE>;
   *applicable = false;
-  return B2S_OK;
+  // q's tensor starts at the halo origin (-3, -3)
+  const TmaField<T> fq = tma_field<T>(q.p - 3 - 3 * q.sj, q.sj, q.sk, q.sb, nk, nb);
+  const TmaField<T> fcx = tma_field<T>(crx.p, crx.sj, crx.sk, crx.sb, nk, nb);
+  const TmaField<T> fxx = tma_field<T>(xfx.p, xfx.sj, xfx.sk, xfx.sb, nk, nb);
+  const TmaField<T> fcy = tma_field<T>(cry.p, cry.sj, cry.sk, cry.sb, nk, nb);
+  const TmaField<T> fyx = tma_field<T>(yfx.p, yfx.sj, yfx.sk, yfx.sb, nk, nb);
+  if (!(fq.ok && fcx.ok && fxx.ok && fcy.ok && fyx.ok)) return B2S_OK;
+
+  CUtensorMap mq, mcx, mxx, mcy, myx;
+  bool ok = make_map<T>(&mq, fq.base, q.sj, q.sk, q.sb, ni + 6 + fq.off, nj + 6, nk, nb, G::BQ, G::RQ) &&
+            make_map<T>(&mcx, fcx.base, crx.sj, crx.sk, crx.sb, ni + 1 + fcx.off, nj, nk, nb, G::BX, G::RX) &&
+            make_map<T>(&mxx, fxx.base, xfx.sj, xfx.sk, xfx.sb, ni + 1 + fxx.off, nj, nk, nb, G::BX, G::RX) &&
+            make_map<T>(&mcy, fcy.base, cry.sj, cry.sk, cry.sb, ni + fcy.off, nj + 1, nk, nb, G::BY, G::RY) &&
+            make_map<T>(&myx, fyx.base, yfx.sj, yfx.sk, yfx.sb, ni + fyx.off, nj + 1, nk, nb, G::BY, G::RY);
+  if (!ok) return B2S_OK;  // driver refused the descriptor: let the direct kernel handle the call
+
+  auto kern = k_fv_tma<T, TI, R, NSTAGE>;
+  static int ctas_per_sm = 0;
+  if (ctas_per_sm == 0) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
+    if (e != cudaSuccess) return set_error((int)e, "fv_tp2d(tma): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    int nblk = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, kern, G::THREADS, G::SMEM_BYTES);
+    if (e != cudaSuccess || nblk < 1) return set_error(e == cudaSuccess ? B2S_EUNSUPPORTED : (int)e, "fv_tp2d(tma): occupancy query failed");
+    ctas_per_sm = nblk;
+  }
+  FvTmaParams<T> P;
+  P.nk = nk;
+  P.nb = nb;
+  P.i0 = i0;
+  P.i1 = i1;
+  P.j0 = j0;
+  P.j1 = j1;
+  P.nstrips = (i1 - i0 + TI - 1) / TI;
+  P.njblk = (j1 - j0 + R - 1) / R;
+  const int64_t nitems = (int64_t)P.nstrips * P.njblk * nk * nb;
+  if (nitems > (int64_t)1 << 30) return B2S_OK;  // beyond the 32-bit item cursor: direct kernel
+  P.nitems = (int)nitems;
+  constexpr int V = G::V;
+  static_assert(TI % V == 0, "tile width must keep the box start alignment from strip to strip");
+  P.c_q = i0 + fq.off, P.sh_q = P.c_q % V;
+  P.c_crx = i0 + fcx.off, P.sh_crx = P.c_crx % V;
+  P.c_xfx = i0 + fxx.off, P.sh_xfx = P.c_xfx % V;
+  P.c_cry = i0 + fcy.off, P.sh_cry = P.c_cry % V;
+  P.c_yfx = i0 + fyx.off, P.sh_yfx = P.c_yfx % V;
+  P.rarea = rarea;
+  P.qout = q_out;
+  const int64_t max_ctas = (int64_t)sm_count() * ctas_per_sm;
+  const int grid = (int)(nitems < max_ctas ? nitems : max_ctas);
+  *applicable = true;
+  kern<<<grid, G::THREADS, G::SMEM_BYTES, s>>>(mq, mcx, mxx, mcy, myx, P);
+  return check_launch("fv_tp2d(tma)");
+}
+
+}  // namespace
+
+template <typename T>
+int fv_tp2d_tma(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j1, F3<const T> q, F3<const T> crx,
+                F3<const T> xfx, F3<const T> cry, F3<const T> yfx, F2<const T> rarea, F3<T> q_out, cudaStream_t s,
+                bool* applicable) {
+  // tile geometry: 128 columns (4 consumer warps + 1 producer warp); rows per stage / ring depth
+  // selectable for tuning with b2s_set_option("fv_tile", n)
+  switch (option("fv_tile", 0)) {
+    case 1:
+      return launch<T, 128, 4, 3>(ni, nj, nk, nb, i0, i1, j0, j1, q, crx, xfx, cry, yfx, rarea, q_out, s, applicable);
+    case 2:
+      return launch<T, 128, 8, 2>(ni, nj, nk, nb, i0, i1, j0, j1, q, crx, xfx, cry, yfx, rarea, q_out, s, applicable);
+    case 3:
+      return launch<T, 128, 8, 3>(ni, nj, nk, nb, i0, i1, j0, j1, q, crx, xfx, cry, yfx, rarea, q_out, s, applicable);
+    case 4:
+      return launch<T, 128, 2, 4>(ni, nj, nk, nb, i0, i1, j0, j1, q, crx, xfx, cry, yfx, rarea, q_out, s, applicable);
+    case 5:
+      return launch<T, 64, 8, 3>(ni, nj, nk, nb, i0, i1, j0, j1, q, crx, xfx, cry, yfx, rarea, q_out, s, applicable);
+    case 6:
+      return launch<T, 128, 16, 2>(ni, nj, nk, nb, i0, i1, j0, j1, q, crx, xfx, cry, yfx, rarea, q_out, s, applicable);
+    default:
+      return launch<T, 128, 4, 2>(ni, nj, nk, nb, i0, i1, j0, j1, q, crx, xfx, cry, yfx, rarea, q_out, s, applicable);
+  }
 }
 
 template int fv_tp2d_tma<double>(int, int, int, int, int, int, int, int, F3<const double>, F3<const double>,

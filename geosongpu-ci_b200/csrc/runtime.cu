@@ -21,7 +21,7 @@ static int g_sms = 0;
 static std::mutex g_mu;
 static std::map<std::string, int> g_options = {
     {"fv_variant", 0},      // 0 auto, 1 direct (L1/L2) kernel, 2 TMA-pipelined kernel
-    {"column_unroll", 0},   // 0 auto
+    {"fv_tile", 0},         // TMA tile geometry (k_fv_tma.cu)
 };
 
 int set_error(int code, const char* fmt, ...) {

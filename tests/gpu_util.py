@@ -13,7 +13,7 @@ def up(a: np.ndarray, align_rows=True) -> torch.Tensor:
 
 def up_batch(arrs, align_rows=True) -> torch.Tensor:
     """list of NumPy [i,j(,k)] -> device field [b,i,j(,k)]."""
-    t = fields.empty(arrs[0].shape, dtype=torch.from_numpy(arrs[0][..., :0].copy()).dtype, batch=len(arrs), align_rows=align_rows)
+    t = fields.empty(arrs[0].shape, dtype=torch.from_numpy(np.empty(0, arrs[0].dtype)).dtype, batch=len(arrs), align_rows=align_rows)
     for b, a in enumerate(arrs):
         t[b].copy_(torch.from_numpy(np.ascontiguousarray(a)))
     return t

@@ -135,7 +135,6 @@ def test_patterns_batched_tiles(st, dtype):
     ni, nj, nk, nb = 12, 10, 9, 6
     Ws = [gen.while_inputs(ni, nj, nk, dtype, cfg=20 + b) for b in range(nb)]
     dW = up_batch(Ws)
-    big = torch.zeros((nb, ni + 6, nj + 6, nk), dtype=tdt(dtype), device="cuda").permute(0, 1, 2, 3)
     store = torch.zeros((nb, nk, nj + 6, ni + 6), dtype=tdt(dtype), device="cuda")
     dO = store.permute(0, 3, 2, 1)[:, 3:-3, 3:-3, :]  # compute window of a halo-3 field
     st.while_in_function(dW, dO)
@@ -144,7 +143,6 @@ def test_patterns_batched_tiles(st, dtype):
         orc.while_in_function_scan(Ws[b], o)
         assert np.array_equal(down(dO[b]), o)
     assert float(store.sum()) == float(dO.sum())  # halo cells untouched (writes stay in the domain)
-    del big
 
 
 # ---- S4 ------------------------------------------------------------------------------------------------
@@ -224,6 +222,28 @@ def test_fv_tp2d_regions_and_unaligned(st, corc, variant):
     _fv_case(st, corc, 40, 30, 3, np.float64, variant, region=(37, 40, 3, 27))
     _fv_case(st, corc, 40, 30, 3, np.float32, variant, region=(5, 5, 0, 30))  # empty
     _fv_case(st, corc, 37, 11, 3, np.float64, variant, align=False)  # odd strides: general path
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shift", [1, 2, 3])
+def test_fv_tp2d_misaligned_base(st, corc, dtype, shift):
+    """Fields whose first element is not 16-byte aligned (views into wider storage) but whose strides
+    are: the TMA path must shift its boxes, not fault."""
+    ni, nj, nk = 70, 9, 3
+    f = gen.fv_inputs(ni, nj, nk, dtype)
+    ref = zeros_like_np((ni, nj, nk), dtype)
+    corc.fv_tp2d(f["q"], f["crx"], f["xfx"], f["cry"], f["yfx"], f["rarea"], ref)
+
+    def shifted(a):
+        wide = up(np.zeros((a.shape[0] + 8,) + a.shape[1:], dtype))
+        view = wide[shift : shift + a.shape[0]]
+        view.copy_(torch.from_numpy(np.ascontiguousarray(a)))
+        return view
+
+    d = {k: shifted(v) for k, v in f.items()}
+    out = shifted(np.zeros((ni, nj, nk), dtype))
+    st.fv_tp2d(d["q"], d["crx"], d["xfx"], d["cry"], d["yfx"], d["rarea"], out)
+    assert_close(down(out), ref, RTOL[dtype], "q_out")
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
