@@ -439,6 +439,9 @@ int fv_tp2d_tma(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j1, 
                 bool* applicable) {
   // tile geometry: 128 columns (4 consumer warps + 1 producer warp); rows per stage / ring depth
   // selectable for tuning with b2s_set_option("fv_tile", n)
+  // narrow rectangles (the west/east boundary strips of the halo-overlap split): 32-column tiles
+  if (i1 - i0 <= 32 && option("fv_tile", 0) == 0)
+    return launch<T, 32, 8, 3>(ni, nj, nk, nb, i0, i1, j0, j1, q, crx, xfx, cry, yfx, rarea, q_out, s, applicable);
   switch (option("fv_tile", 0)) {
     case 1:
       return launch<T, 128, 4, 3>(ni, nj, nk, nb, i0, i1, j0, j1, q, crx, xfx, cry, yfx, rarea, q_out, s, applicable);
@@ -453,7 +456,10 @@ int fv_tp2d_tma(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j1, 
     case 6:
       return launch<T, 128, 16, 2>(ni, nj, nk, nb, i0, i1, j0, j1, q, crx, xfx, cry, yfx, rarea, q_out, s, applicable);
     default:
-      return launch<T, 128, 4, 2>(ni, nj, nk, nb, i0, i1, j0, j1, q, crx, xfx, cry, yfx, rarea, q_out, s, applicable);
+      // measured on C384x72 (profiles/): fp64 is fastest with 4-row stages (3 CTAs/SM), fp32 with 8-row stages
+      if (sizeof(T) == 8)
+        return launch<T, 128, 4, 2>(ni, nj, nk, nb, i0, i1, j0, j1, q, crx, xfx, cry, yfx, rarea, q_out, s, applicable);
+      return launch<T, 128, 8, 2>(ni, nj, nk, nb, i0, i1, j0, j1, q, crx, xfx, cry, yfx, rarea, q_out, s, applicable);
   }
 }
 

@@ -1,0 +1,74 @@
+"""-m gpu: the CUDA halo_move kernel through the same link tables the NCCL path uses (virtual GPUs on
+one device), and the interior/frame split of the transport step against the unsplit stencil."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from b200stencil.halo.partitioner import CubedSpherePartitioner, layout_for  # noqa: E402
+from b200stencil.halo.transport import FvTransport, split_regions  # noqa: E402
+from b200stencil.halo.updater import exchange_in_process  # noqa: E402
+
+from halo_util import batch_field, check_field  # noqa: E402
+
+
+@pytest.mark.parametrize("n_gpus", [1, 2, 4, 8])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_global_id_exchange_cuda(n_gpus, dtype):
+    N, nk = 24, 3
+    part = CubedSpherePartitioner(N, layout_for(n_gpus))
+    fields = [batch_field(part, n_gpus, g, nk, device="cuda", dtype=dtype, pad=2) for g in range(n_gpus)]
+    exchange_in_process(part, n_gpus, fields)
+    torch.cuda.synchronize()
+    for g in range(n_gpus):
+        check_field(part, n_gpus, g, fields[g], nk)
+
+
+@pytest.mark.parametrize("shape", [(192, 40), (140, 20), (64, 64), (20, 9)])
+def test_region_split_equals_full(shape):
+    from b200stencil import fields as F
+    from b200stencil import stencils
+
+    ni, nj = shape
+    nk, nb = 3, 2
+    g = torch.Generator(device="cuda").manual_seed(1)
+    mk = lambda s, lo, hi: F.empty(s, torch.float64, batch=nb).uniform_(lo, hi, generator=g)  # noqa: E731
+    q = mk((ni + 6, nj + 6, nk), 0.5, 1.5)
+    crx, cry = mk((ni + 1, nj, nk), -0.9, 0.9), mk((ni, nj + 1, nk), -0.9, 0.9)
+    xfx, yfx = mk((ni + 1, nj, nk), -1, 1), mk((ni, nj + 1, nk), -1, 1)
+    rarea = mk((ni, nj), 0.9, 1.1)
+    full = F.zeros((ni, nj, nk), batch=nb)
+    stencils.fv_tp2d(q, crx, xfx, cry, yfx, rarea, full)
+    split = F.zeros((ni, nj, nk), batch=nb)
+    interior, frame = split_regions(ni, nj)
+    cover = np.zeros((ni, nj), int)
+    for r in [interior] + frame:
+        if r[1] > r[0] and r[3] > r[2]:
+            stencils.fv_tp2d(q, crx, xfx, cry, yfx, rarea, split, region=r)
+            cover[r[0] : r[1], r[2] : r[3]] += 1
+    assert np.all(cover == 1), "interior + frame must tile the domain exactly once"
+    assert torch.equal(full, split)  # same kernels, same arithmetic: bit-identical
+
+
+def test_transport_single_gpu_fills_halos_then_steps():
+    """G = 1: six tiles on one device; the step must equal 'exchange, then stencil'."""
+    from b200stencil import fields as F
+    from b200stencil import stencils
+
+    N, nk = 24, 2
+    part = CubedSpherePartitioner(N)
+    tr = FvTransport(part, 1, 0)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    mk = lambda s, lo, hi: F.empty(s, torch.float64, batch=6).uniform_(lo, hi, generator=g)  # noqa: E731
+    q = mk((N + 6, N + 6, nk), 0.5, 1.5)
+    crx, cry = mk((N + 1, N, nk), -0.9, 0.9), mk((N, N + 1, nk), -0.9, 0.9)
+    xfx, yfx, rarea = mk((N + 1, N, nk), -1, 1), mk((N, N + 1, nk), -1, 1), mk((N, N), 0.9, 1.1)
+    q2 = q.clone()
+    out1, out2 = F.zeros((N, N, nk), batch=6), F.zeros((N, N, nk), batch=6)
+    tr.step(q, crx, xfx, cry, yfx, rarea, out1)
+    exchange_in_process(part, 1, [q2])
+    stencils.fv_tp2d(q2, crx, xfx, cry, yfx, rarea, out2)
+    assert torch.equal(out1, out2)
+    # a halo cell now holds its neighbour's interior value: west halo of tile 1 <- north edge of tile 5
+    assert torch.equal(q[0, 2, 3:-3, :], q[4, 3:-3, -4, :].flip(0))
