@@ -10,9 +10,14 @@ import torch
 from . import harness, workloads
 
 
-def run_one(stencil: str, config: str, dtype, iters: int, warmup: int, graph: bool = False) -> dict:
-    tiles, n, nk = workloads.CONFIGS[config]
-    wl = workloads.make(stencil, tiles, n, nk, dtype)
+def run_one(stencil: str, config: str, dtype, iters: int, warmup: int, graph: bool = False, sub=None) -> dict:
+    if sub:  # explicit sub-domain batch: ni,nj,nb,nk
+        ni, nj, tiles, nk = sub
+        wl = workloads.make(stencil, tiles, ni, nk, dtype, ni=ni, nj=nj)
+        config = f"{tiles}x{ni}x{nj}x{nk}"
+    else:
+        tiles, n, nk = workloads.CONFIGS[config]
+        wl = workloads.make(stencil, tiles, n, nk, dtype)
     if graph:
         t = harness.time_graph(wl.run, rotate=wl.slots, launches_per_graph=max(wl.slots * 4, 16), iters=iters, warmup=warmup)
     else:
@@ -42,6 +47,7 @@ def main(argv=None) -> int:
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--sub", default=None, help="explicit sub-domain batch ni,nj,nb,nk instead of a named config")
     ap.add_argument("--graph", action="store_true", help="time CUDA-graph replays (removes host launch overhead)")
     ap.add_argument("--option", action="append", default=[], help="libb200stencil option name=value")
     ns = ap.parse_args(argv)
@@ -55,7 +61,8 @@ def main(argv=None) -> int:
         for d in ns.dtypes.split(","):
             dtype = torch.float64 if d == "f64" else torch.float32
             cfg = ns.config or workloads.DEFAULT_CONFIG[stencil]
-            row = run_one(stencil, cfg, dtype, ns.iters, ns.warmup, ns.graph)
+            sub = tuple(int(x) for x in ns.sub.split(",")) if ns.sub else None
+            row = run_one(stencil, cfg, dtype, ns.iters, ns.warmup, ns.graph, sub)
             if ns.option:
                 row["options"] = ns.option
             rows.append(row)

@@ -34,23 +34,53 @@ def split_regions(ni: int, nj: int, halo: int = 3, side: int = 32) -> Tuple[Rect
 
 
 class FvTransport:
+    """``exchange`` = "nccl" (packed strips + grouped NCCL send/recv, optionally overlapped with the
+    interior) or "p2p" (device barrier + one peer-memory pull kernel; ``q`` must then be the field of
+    the :class:`~b200stencil.halo.p2p.SymmetricField` given as ``symmetric_q``)."""
+
     def __init__(self, part: CubedSpherePartitioner, n_gpus: int, gpu: int, process_group=None,
-                 overlap: bool = True, side: int = 32):
+                 overlap: bool = True, side: int = 32, exchange: str = "nccl", symmetric_q=None):
         self.part, self.n_gpus, self.gpu = part, n_gpus, gpu
+        self.exchange = exchange
         self.updater = HaloUpdater(part, n_gpus, gpu, process_group=process_group)
+        self.p2p = None
+        if exchange == "p2p":
+            from .p2p import P2PHaloUpdater
+
+            if symmetric_q is None:
+                raise ValueError('exchange="p2p" needs the SymmetricField that holds q')
+            self.p2p = P2PHaloUpdater(part, n_gpus, gpu, symmetric_q)
+            overlap = False
         self.overlap = overlap and bool(self.updater.plan.peers)
         self.interior, self.frame = split_regions(part.nx, part.ny, part.halo, side)
-        self.kernel_launches_per_step = 0
+        self._calls = {}
+
+    def calls(self, q, crx, xfx, cry, yfx, rarea, q_out, q_out_halo: int = 0):
+        """(full, interior, [frame...]) PreparedCalls for this set of fields, marshalled once."""
+        fs = (q, crx, xfx, cry, yfx, rarea, q_out)
+        key = tuple((t.data_ptr(), tuple(t.stride()), tuple(t.shape)) for t in fs) + (q_out_halo,)
+        if key not in self._calls:
+            mk = lambda region: stencils.prepare_fv_tp2d(*fs, region=region, q_out_halo=q_out_halo)  # noqa: E731
+            interior = mk(self.interior) if self.interior[1] > self.interior[0] else None
+            self._calls[key] = (mk(None), interior, [mk(r) for r in self.frame])
+        return self._calls[key]
 
     def step(self, q, crx, xfx, cry, yfx, rarea, q_out, q_out_halo: int = 0) -> None:
         """q (halo-padded batch field) -> q_out; q's halos are refreshed from the neighbours first."""
+        full, interior, frame = self.calls(q, crx, xfx, cry, yfx, rarea, q_out, q_out_halo)
+        if self.p2p is not None:
+            if q.data_ptr() != self.p2p.sfield.field.data_ptr():
+                raise ValueError("p2p exchange: q is not the symmetric field this transport was built for")
+            self.p2p.update()
+            full()
+            return
         if not self.overlap:
             self.updater.update(q)
-            stencils.fv_tp2d(q, crx, xfx, cry, yfx, rarea, q_out, q_out_halo=q_out_halo)
+            full()
             return
         self.updater.start(q)
-        if self.interior[1] > self.interior[0]:
-            stencils.fv_tp2d(q, crx, xfx, cry, yfx, rarea, q_out, region=self.interior, q_out_halo=q_out_halo)
+        if interior is not None:
+            interior()
         self.updater.wait()
-        for rect in self.frame:
-            stencils.fv_tp2d(q, crx, xfx, cry, yfx, rarea, q_out, region=rect, q_out_halo=q_out_halo)
+        for call in frame:
+            call()

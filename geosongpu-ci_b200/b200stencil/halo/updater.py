@@ -26,13 +26,13 @@ import torch
 from .partitioner import CubedSpherePartitioner, Link
 
 LINK_WORDS = 10
-Mover = Callable[[torch.Tensor, int, torch.Tensor, torch.Tensor], None]
+Mover = Callable[..., None]  # mover(links, nk, src, dst, max_strip)
 
 
-def _cuda_mover(links: torch.Tensor, nk: int, src: torch.Tensor, dst: torch.Tensor) -> None:
+def _cuda_mover(links: torch.Tensor, nk: int, src: torch.Tensor, dst: torch.Tensor, max_strip: int = 0) -> None:
     from .. import stencils
 
-    stencils.halo_move(links, nk, src, dst)
+    stencils.halo_move(links, nk, src, dst, max_strip)
 
 
 class FieldGeometry:
@@ -148,8 +148,35 @@ class HaloUpdater:
             prep["send_buf"] = torch.empty(max(t["send_total"], 1), dtype=field.dtype, device=dev)
             prep["recv_buf"] = torch.empty(max(t["recv_total"], 1), dtype=field.dtype, device=dev)
             prep["nk"] = geo.nk
+            for k in ("local", "pack", "unpack"):  # largest strip of each table, known on the host
+                prep["max_" + k] = int((t[k][:, 8] * t[k][:, 9]).max()) if len(t[k]) else 0
             self._cache[key] = prep
         return self._cache[key]
+
+    def _movers(self, prep: dict, field: torch.Tensor, flat: torch.Tensor):
+        """(pack, local, unpack) callables for this field.  With the CUDA mover they are PreparedCalls
+        bound to the field's storage (argument marshalling done once, ~1 us of host time per launch)."""
+        if self.mover is not _cuda_mover:
+            return (
+                lambda: self.mover(prep["pack"], prep["nk"], flat, prep["send_buf"], prep["max_pack"]),
+                lambda: self.mover(prep["local"], prep["nk"], flat, flat, prep["max_local"]),
+                lambda: self.mover(prep["unpack"], prep["nk"], prep["recv_buf"], flat, prep["max_unpack"]),
+            )
+        key = (field.data_ptr(), field.dtype)
+        calls = prep.setdefault("calls", {})
+        if key not in calls:
+            from .. import stencils
+
+            noop = lambda: None  # noqa: E731
+            mk = lambda tbl, src, dst, mx: (  # noqa: E731
+                stencils.prepare_halo_move(prep[tbl], prep["nk"], src, dst, prep[mx]) if len(prep[tbl]) else noop
+            )
+            calls[key] = (
+                mk("pack", flat, prep["send_buf"], "max_pack"),
+                mk("local", flat, flat, "max_local"),
+                mk("unpack", prep["recv_buf"], flat, "max_unpack"),
+            )
+        return calls[key]
 
     def _flat(self, field: torch.Tensor) -> torch.Tensor:
         """1-D alias of the storage behind ``field`` starting at its first element (what link offsets index)."""
@@ -174,8 +201,9 @@ class HaloUpdater:
             ctx.__enter__()
         try:
             reqs = []
+            pack, local, unpack = self._movers(prep, field, flat)
             if self.plan.peers:
-                self.mover(prep["pack"], prep["nk"], flat, prep["send_buf"])
+                pack()
                 ops = []
                 for peer in self.plan.peers:
                     so, sn = prep["send_seg"][peer]
@@ -188,8 +216,8 @@ class HaloUpdater:
                 reqs = dist.batch_isend_irecv(ops) if ops else []
                 self.bytes_sent_per_update = prep["send_total"] * field.element_size()
             # same-GPU neighbours: straight copies, concurrent with the transfer
-            self.mover(prep["local"], prep["nk"], flat, flat)
-            self._pending = (prep, flat, reqs, field)
+            local()
+            self._pending = (prep, flat, reqs, field, unpack)
         finally:
             if ctx is not None:
                 ctx.__exit__(None, None, None)
@@ -198,7 +226,7 @@ class HaloUpdater:
         """Complete the exchange: unpack received strips; the current stream then sees full halos."""
         if self._pending is None:
             return
-        prep, flat, reqs, field = self._pending
+        prep, flat, reqs, field, unpack = self._pending
         self._pending = None
         cuda = field.is_cuda
         on_comm = cuda and self._comm_stream is not None and self.plan.peers
@@ -206,13 +234,13 @@ class HaloUpdater:
             with torch.cuda.stream(self._comm_stream):
                 for r in reqs:
                     r.wait()
-                self.mover(prep["unpack"], prep["nk"], prep["recv_buf"], flat)
+                unpack()
             torch.cuda.current_stream(field.device).wait_stream(self._comm_stream)
         else:
             for r in reqs:
                 r.wait()
             if self.plan.peers:
-                self.mover(prep["unpack"], prep["nk"], prep["recv_buf"], flat)
+                unpack()
 
     def update(self, field: torch.Tensor) -> None:
         self.start(field)
@@ -233,7 +261,7 @@ def exchange_in_process(part: CubedSpherePartitioner, n_gpus: int, fields: Seque
     flats = [u._flat(f) for u, f in zip(ups, fields)]
     for g in range(n_gpus):
         if ups[g].plan.peers:
-            mover(preps[g]["pack"], preps[g]["nk"], flats[g], preps[g]["send_buf"])
+            mover(preps[g]["pack"], preps[g]["nk"], flats[g], preps[g]["send_buf"], preps[g]["max_pack"])
     for g in range(n_gpus):
         for peer in ups[g].plan.peers:
             so, sn = preps[g]["send_seg"][peer]
@@ -241,6 +269,6 @@ def exchange_in_process(part: CubedSpherePartitioner, n_gpus: int, fields: Seque
             assert sn == rn, "send and receive segments of a GPU pair must agree"
             preps[peer]["recv_buf"][ro : ro + rn].copy_(preps[g]["send_buf"][so : so + sn])
     for g in range(n_gpus):
-        mover(preps[g]["local"], preps[g]["nk"], flats[g], flats[g])
+        mover(preps[g]["local"], preps[g]["nk"], flats[g], flats[g], preps[g]["max_local"])
         if ups[g].plan.peers:
-            mover(preps[g]["unpack"], preps[g]["nk"], preps[g]["recv_buf"], flats[g])
+            mover(preps[g]["unpack"], preps[g]["nk"], preps[g]["recv_buf"], flats[g], preps[g]["max_unpack"])

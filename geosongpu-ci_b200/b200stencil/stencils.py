@@ -75,6 +75,20 @@ def cloud_top(ql, ktop, ql_min: float = 1.0e-8, stream=None) -> None:
     _abi.call("cloud_top", _abi.precision_of(ql), dict(ni=ni, nj=nj, nk=nk, nb=nb, ql_min=float(ql_min), ql=ql, ktop=ktop), stream)
 
 
+def prepare_fv_tp2d(q, crx, xfx, cry, yfx, rarea, q_out, region=None, q_out_halo: int = 0) -> "_abi.PreparedCall":
+    """fv_tp2d with its arguments marshalled once (see :class:`_abi.PreparedCall`)."""
+    h = FV_HALO
+    nip, njp, nk, nb = shape3(q)
+    ni, nj = nip - 2 * h, njp - 2 * h
+    i0, i1, j0, j1 = (0, ni, 0, nj) if region is None else region
+    return _abi.prepare(
+        "fv_tp2d", _abi.precision_of(q),
+        dict(ni=ni, nj=nj, nk=nk, nb=nb, i0=i0, i1=i1, j0=j0, j1=j1, q=q, crx=crx, xfx=xfx, cry=cry, yfx=yfx,
+             rarea=rarea, q_out=q_out),
+        origins={"q": (h, h, 0), "q_out": (q_out_halo, q_out_halo, 0)},
+    )  # fmt: skip
+
+
 def fv_tp2d(q, crx, xfx, cry, yfx, rarea, q_out, region=None, q_out_halo: int = 0, stream=None) -> None:
     """S5 (spec: oracle/numpy_oracle.py fv_tp2d) -- K5 (csrc/k_fv*.cu).
 
@@ -83,16 +97,7 @@ def fv_tp2d(q, crx, xfx, cry, yfx, rarea, q_out, region=None, q_out_halo: int = 
     ``region`` = (i0, i1, j0, j1) restricts the update to a sub-rectangle (interior / boundary
     split for halo-exchange overlap); default is the whole domain.
     """
-    h = FV_HALO
-    nip, njp, nk, nb = shape3(q)
-    ni, nj = nip - 2 * h, njp - 2 * h
-    i0, i1, j0, j1 = (0, ni, 0, nj) if region is None else region
-    _abi.call(
-        "fv_tp2d", _abi.precision_of(q),
-        dict(ni=ni, nj=nj, nk=nk, nb=nb, i0=i0, i1=i1, j0=j0, j1=j1, q=q, crx=crx, xfx=xfx, cry=cry, yfx=yfx,
-             rarea=rarea, q_out=q_out),
-        stream, origins={"q": (h, h, 0), "q_out": (q_out_halo, q_out_halo, 0)},
-    )  # fmt: skip
+    prepare_fv_tp2d(q, crx, xfx, cry, yfx, rarea, q_out, region, q_out_halo)(stream)
 
 
 def pe_prefix(delp, ptop: float, pe, stream=None) -> None:
@@ -116,9 +121,24 @@ def tridiag(a, b, c, d, x, w=None, stream=None) -> None:
     _abi.call("tridiag", _abi.precision_of(b), dict(ni=ni, nj=nj, nk=nk, nb=nb, a=a, b=b, c=c, d=d, w=w, x=x), stream)
 
 
-def halo_move(links, nk: int, src, dst, stream=None) -> None:
-    """K7 (csrc/k_halo.cu): run the affine strip copies described by ``links`` (int64 [nlinks, 10])."""
-    nlinks = int(links.shape[0])
-    if nlinks == 0:
+def halo_move(links, nk: int, src, dst, max_strip: int, stream=None) -> None:
+    """K7 (csrc/k_halo.cu): run the affine strip copies described by ``links`` (int64 [nlinks, 10]);
+    ``max_strip`` = the largest nd*np of the table (sizes the grid without a device read-back)."""
+    if int(links.shape[0]) == 0:
         return
-    _abi.call("halo_move", _abi.precision_of(src), dict(nlinks=nlinks, nk=int(nk), links=links, src=src, dst=dst), stream)
+    prepare_halo_move(links, nk, src, dst, max_strip)(stream)
+
+
+def prepare_halo_move(links, nk: int, src, dst, max_strip: int) -> "_abi.PreparedCall":
+    return _abi.prepare(
+        "halo_move", _abi.precision_of(src),
+        dict(nlinks=int(links.shape[0]), nk=int(nk), max_strip=int(max_strip), links=links, src=src, dst=dst),
+    )  # fmt: skip
+
+
+def prepare_halo_pull(links, nk: int, dst, max_strip: int) -> "_abi.PreparedCall":
+    """One-kernel halo update over peer memory (csrc/k_halo.cu halo_pull); links int64 [nlinks, 11]."""
+    return _abi.prepare(
+        "halo_pull", _abi.precision_of(dst),
+        dict(nlinks=int(links.shape[0]), nk=int(nk), max_strip=int(max_strip), links=links, dst=dst),
+    )  # fmt: skip

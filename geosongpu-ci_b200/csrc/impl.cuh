@@ -38,7 +38,10 @@ int tridiag(int ni, int nj, int nk, int nb, F3<const T> a, F3<const T> b, F3<con
             F3<T> x, cudaStream_t s);
 
 template <typename T>
-int halo_move(int nlinks, int nk, const int64_t* links, const T* src, T* dst, cudaStream_t s);
+int halo_move(int nlinks, int nk, int max_strip, const int64_t* links, const T* src, T* dst, cudaStream_t s);
+
+template <typename T>
+int halo_pull(int nlinks, int nk, int max_strip, const int64_t* links, T* dst, cudaStream_t s);
 
 }  // namespace impl
 }  // namespace b2s

@@ -30,8 +30,8 @@ __global__ void __launch_bounds__(256) k_fv_direct(int nk, int i0, int i1, int j
     const T al_p1 = ppm_al(m1, q0, p1, p2), al_p2 = ppm_al(q0, p1, p2, p3);
     const T* cp = crx.at(i, j, k, b);
     const T* xp = xfx.at(i, j, k, b);
-    fx_lo = ppm_flux_from_al(m1, q0, al_m1, al_0, al_p1, __ldg(cp)) * __ldg(xp);
-    fx_hi = ppm_flux_from_al(q0, p1, al_0, al_p1, al_p2, __ldg(cp + 1)) * __ldg(xp + 1);
+    fx_lo = mul_rn(ppm_flux_from_al(m1, q0, al_m1, al_0, al_p1, __ldg(cp)), __ldg(xp));
+    fx_hi = mul_rn(ppm_flux_from_al(q0, p1, al_0, al_p1, al_p2, __ldg(cp + 1)), __ldg(xp + 1));
   }
   // y direction
   T fy_lo, fy_hi;
@@ -43,11 +43,11 @@ __global__ void __launch_bounds__(256) k_fv_direct(int nk, int i0, int i1, int j
     const T al_p1 = ppm_al(m1, q0, p1, p2), al_p2 = ppm_al(q0, p1, p2, p3);
     const T* cp = cry.at(i, j, k, b);
     const T* yp = yfx.at(i, j, k, b);
-    fy_lo = ppm_flux_from_al(m1, q0, al_m1, al_0, al_p1, __ldg(cp)) * __ldg(yp);
-    fy_hi = ppm_flux_from_al(q0, p1, al_0, al_p1, al_p2, __ldg(cp + cry.sj)) * __ldg(yp + yfx.sj);
+    fy_lo = mul_rn(ppm_flux_from_al(m1, q0, al_m1, al_0, al_p1, __ldg(cp)), __ldg(yp));
+    fy_hi = mul_rn(ppm_flux_from_al(q0, p1, al_0, al_p1, al_p2, __ldg(cp + cry.sj)), __ldg(yp + yfx.sj));
   }
   const T ra = __ldg(rarea.at(i, j, b));
-  __stcs(qout.at(i, j, k, b), q0 - ra * ((fx_hi - fx_lo) + (fy_hi - fy_lo)));
+  __stcs(qout.at(i, j, k, b), fv_update(q0, ra, fx_lo, fx_hi, fy_lo, fy_hi));
 }
 
 template <typename T>

@@ -255,22 +255,22 @@ __global__ void __launch_bounds__(TI + 32) k_fv_tma(const __grid_constant__ CUte
     T fy_lo;
     {
       const T al_m1 = ppm_al(qs[0 * G::BQ + 3], qm2, qm1, q0);
-      fy_lo = ppm_flux_from_al(qm1, q0, al_m1, al_0, al_p1, cys[0]) * yfs[0];
+      fy_lo = mul_rn(ppm_flux_from_al(qm1, q0, al_m1, al_0, al_p1, cys[0]), yfs[0]);
     }
 
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const T qp3 = qs[(r + 6) * G::BQ + 3];
       const T al_p2 = ppm_al(q0, qp1, qp2, qp3);
-      const T fy_hi = ppm_flux_from_al(q0, qp1, al_0, al_p1, al_p2, cys[(r + 1) * G::BY]) * yfs[(r + 1) * G::BY];
+      const T fy_hi = mul_rn(ppm_flux_from_al(q0, qp1, al_0, al_p1, al_p2, cys[(r + 1) * G::BY]), yfs[(r + 1) * G::BY]);
       // x direction on row js + r (shared-memory row r + 3)
       const T* row = qs + (r + 3) * G::BQ;
       const T xm3 = row[0], xm2 = row[1], xm1 = row[2], xp1 = row[4], xp2 = row[5], xp3 = row[6];
       const T ax_m1 = ppm_al(xm3, xm2, xm1, q0), ax_0 = ppm_al(xm2, xm1, q0, xp1);
       const T ax_p1 = ppm_al(xm1, q0, xp1, xp2), ax_p2 = ppm_al(q0, xp1, xp2, xp3);
-      const T fx_lo = ppm_flux_from_al(xm1, q0, ax_m1, ax_0, ax_p1, cxs[r * G::BX]) * xfs[r * G::BX];
-      const T fx_hi = ppm_flux_from_al(q0, xp1, ax_0, ax_p1, ax_p2, cxs[r * G::BX + 1]) * xfs[r * G::BX + 1];
-      if (r < nrows) __stcs(outp + (int64_t)r * P.qout.sj, q0 - ra[r] * ((fx_hi - fx_lo) + (fy_hi - fy_lo)));
+      const T fx_lo = mul_rn(ppm_flux_from_al(xm1, q0, ax_m1, ax_0, ax_p1, cxs[r * G::BX]), xfs[r * G::BX]);
+      const T fx_hi = mul_rn(ppm_flux_from_al(q0, xp1, ax_0, ax_p1, ax_p2, cxs[r * G::BX + 1]), xfs[r * G::BX + 1]);
+      if (r < nrows) __stcs(outp + (int64_t)r * P.qout.sj, fv_update(q0, ra[r], fx_lo, fx_hi, fy_lo, fy_hi));
       // slide the window one row down
       qm1 = q0;
       q0 = qp1;
@@ -433,33 +433,64 @@ int launch(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j1, F3<co
 
 }  // namespace
 
+#define B2S_FV_ARGS ni, nj, nk, nb, i0, i1, j0, j1, q, crx, xfx, cry, yfx, rarea, q_out, s, applicable
+
+template <typename T, int TI>
+int launch_rows_stages(int rows, int stages, int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j1,
+                       F3<const T> q, F3<const T> crx, F3<const T> xfx, F3<const T> cry, F3<const T> yfx,
+                       F2<const T> rarea, F3<T> q_out, cudaStream_t s, bool* applicable) {
+  if (rows == 8) return stages == 3 ? launch<T, TI, 8, 3>(B2S_FV_ARGS) : launch<T, TI, 8, 2>(B2S_FV_ARGS);
+  return stages == 3 ? launch<T, TI, 4, 3>(B2S_FV_ARGS) : launch<T, TI, 4, 2>(B2S_FV_ARGS);
+}
+
 template <typename T>
 int fv_tp2d_tma(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j1, F3<const T> q, F3<const T> crx,
                 F3<const T> xfx, F3<const T> cry, F3<const T> yfx, F2<const T> rarea, F3<T> q_out, cudaStream_t s,
                 bool* applicable) {
-  // tile geometry: 128 columns (4 consumer warps + 1 producer warp); rows per stage / ring depth
-  // selectable for tuning with b2s_set_option("fv_tile", n)
-  // narrow rectangles (the west/east boundary strips of the halo-overlap split): 32-column tiles
-  if (i1 - i0 <= 32 && option("fv_tile", 0) == 0)
-    return launch<T, 32, 8, 3>(ni, nj, nk, nb, i0, i1, j0, j1, q, crx, xfx, cry, yfx, rarea, q_out, s, applicable);
-  switch (option("fv_tile", 0)) {
-    case 1:
-      return launch<T, 128, 4, 3>(ni, nj, nk, nb, i0, i1, j0, j1, q, crx, xfx, cry, yfx, rarea, q_out, s, applicable);
-    case 2:
-      return launch<T, 128, 8, 2>(ni, nj, nk, nb, i0, i1, j0, j1, q, crx, xfx, cry, yfx, rarea, q_out, s, applicable);
-    case 3:
-      return launch<T, 128, 8, 3>(ni, nj, nk, nb, i0, i1, j0, j1, q, crx, xfx, cry, yfx, rarea, q_out, s, applicable);
-    case 4:
-      return launch<T, 128, 2, 4>(ni, nj, nk, nb, i0, i1, j0, j1, q, crx, xfx, cry, yfx, rarea, q_out, s, applicable);
-    case 5:
-      return launch<T, 64, 8, 3>(ni, nj, nk, nb, i0, i1, j0, j1, q, crx, xfx, cry, yfx, rarea, q_out, s, applicable);
-    case 6:
-      return launch<T, 128, 16, 2>(ni, nj, nk, nb, i0, i1, j0, j1, q, crx, xfx, cry, yfx, rarea, q_out, s, applicable);
+  // Tile geometry.  Width TI = consumer threads per CTA (+ 1 producer warp); widths on offer: 32
+  // (narrow boundary strips), 64, 96, 128, 192 columns; R rows per stage; NSTAGE-deep ring.
+  // Automatic choice, from the sweeps in profiles/r01_fv_tile_sweep.md:
+  //   width a multiple of 128 (C384 tiles, 384-wide sub-domains): 128 x 4 rows (fp64) / 8 rows (fp32)
+  //   width a multiple of 64 only (the 192-wide sub-domains of the 8-GPU layout): 64 x 8 rows --
+  //     no half-empty tile, 4 CTAs/SM; 6.2 TB/s vs 5.2 TB/s for 128-column tiles on 3x192x192x72
+  //   anything else: the width among 128/96/64 that wastes the fewest columns, ties towards 128.
+  // b2s_set_option("fv_ti" | "fv_rows" | "fv_stages", n) overrides each for tuning.
+  const int w = i1 - i0;
+  int ti = option("fv_ti", 0);
+  int rows = option("fv_rows", 0), stages = option("fv_stages", 0);
+  if (ti == 0) {
+    if (w <= 32) {
+      ti = 32;
+    } else if (w % 128 == 0) {
+      ti = 128;
+    } else if (w % 64 == 0) {
+      ti = 64;
+      if (rows == 0) rows = 8;
+    } else {
+      const int cand[3] = {128, 96, 64};
+      int best_waste = 1 << 30;
+      for (int c : cand) {
+        const int waste = (w + c - 1) / c * c - w;
+        if (waste < best_waste) {
+          best_waste = waste;
+          ti = c;
+        }
+      }
+    }
+  }
+  if (rows == 0) rows = sizeof(T) == 8 ? 4 : 8;
+  if (stages == 0) stages = 2;
+  switch (ti) {
+    case 32:
+      return launch<T, 32, 8, 3>(B2S_FV_ARGS);
+    case 64:
+      return launch_rows_stages<T, 64>(rows, stages, B2S_FV_ARGS);
+    case 96:
+      return launch_rows_stages<T, 96>(rows, stages, B2S_FV_ARGS);
+    case 192:
+      return launch_rows_stages<T, 192>(rows, stages, B2S_FV_ARGS);
     default:
-      // measured on C384x72 (profiles/): fp64 is fastest with 4-row stages (3 CTAs/SM), fp32 with 8-row stages
-      if (sizeof(T) == 8)
-        return launch<T, 128, 4, 2>(ni, nj, nk, nb, i0, i1, j0, j1, q, crx, xfx, cry, yfx, rarea, q_out, s, applicable);
-      return launch<T, 128, 8, 2>(ni, nj, nk, nb, i0, i1, j0, j1, q, crx, xfx, cry, yfx, rarea, q_out, s, applicable);
+      return launch_rows_stages<T, 128>(rows, stages, B2S_FV_ARGS);
   }
 }
 

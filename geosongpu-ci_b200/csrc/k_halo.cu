@@ -15,32 +15,93 @@ namespace impl {
 
 static constexpr int kLinkWords = 10;
 
+// grid = (strip chunks, k, link): one thread per strip element, 32-bit index arithmetic only.
+// The faster-varying thread index follows whichever of (d, p) is contiguous on the SOURCE side,
+// so reads coalesce for north/south strips (p along i) and stay sector-dense for west/east ones
+// (d along i: 3 adjacent elements).
 template <typename T>
 __global__ void __launch_bounds__(256) k_halo_move(int nk, const int64_t* __restrict__ links, const T* src, T* dst) {
-  const int64_t* L = links + (int64_t)blockIdx.y * kLinkWords;
+  const int64_t* L = links + (int64_t)blockIdx.z * kLinkWords;
   const int nd = (int)L[8], np = (int)L[9];
-  const int64_t total = (int64_t)nd * np * nk;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int p = (int)(t % np);
-    const int64_t r = t / np;
-    const int d = (int)(r % nd);
-    const int k = (int)(r / nd);
-    dst[L[4] + d * L[5] + p * L[6] + k * L[7]] = src[L[0] + d * L[1] + p * L[2] + k * L[3]];
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= nd * np) return;
+  const int64_t ssd = L[1], ssp = L[2];
+  int d, p;
+  if (ssd == 1 || ssd == -1) {  // depth runs along i on the source side
+    d = t % nd;
+    p = t / nd;
+  } else {
+    p = t % np;
+    d = t / np;
   }
+  const int k = blockIdx.y;
+  dst[L[4] + d * L[5] + p * L[6] + k * L[7]] = src[L[0] + d * ssd + p * ssp + k * L[3]];
 }
 
 template <typename T>
-int halo_move(int nlinks, int nk, const int64_t* links, const T* src, T* dst, cudaStream_t s) {
+int halo_move(int nlinks, int nk, const int64_t* links, const T* src, T* dst, cudaStream_t s, int max_strip) {
   B2S_ARGCHECK(nlinks >= 0 && nk > 0, "halo_move: bad sizes nlinks=%d nk=%d", nlinks, nk);
   if (nlinks == 0) return B2S_OK;
   B2S_ARGCHECK(links && src && dst, "halo_move: null pointer");
-  dim3 grid(16, nlinks);
+  B2S_ARGCHECK(nk <= 65535 && nlinks <= 65535, "halo_move: grid too large (nk=%d, nlinks=%d)", nk, nlinks);
+  dim3 grid((max_strip + 255) / 256, nk, nlinks);
   k_halo_move<T><<<grid, 256, 0, s>>>(nk, links, src, dst);
   return check_launch("halo_move");
 }
 
-template int halo_move<double>(int, int, const int64_t*, const double*, double*, cudaStream_t);
-template int halo_move<float>(int, int, const int64_t*, const float*, float*, cudaStream_t);
+template <typename T>
+int halo_move(int nlinks, int nk, int max_strip, const int64_t* links, const T* src, T* dst, cudaStream_t s) {
+  B2S_ARGCHECK(max_strip > 0, "halo_move: max_strip must be the largest nd*np of the table, got %d", max_strip);
+  return halo_move<T>(nlinks, nk, links, src, dst, s, max_strip);
+}
+
+// -------------------------------------------------------------------------------------------
+// halo_pull: the whole halo update of a GPU as ONE kernel over NVLink peer memory.
+// Same strip copies as halo_move, but every link carries the BASE ADDRESS of its source buffer in
+// word [10]: the field of the GPU that owns the neighbouring sub-domain, mapped into this process
+// (torch symmetric memory / CUDA IPC), or this GPU's own field for same-GPU neighbours.  Loads on a
+// peer address travel over NVLink (SASS is an ordinary LDG; the address aperture routes it), so
+// there is no pack buffer, no NCCL launch and no unpack: ordering against the peers' writes is a
+// device-side barrier issued before this kernel (halo/p2p.py).
+// -------------------------------------------------------------------------------------------
+static constexpr int kPullWords = 11;
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_halo_pull(int nk, const int64_t* __restrict__ links, T* dst) {
+  const int64_t* L = links + (int64_t)blockIdx.z * kPullWords;
+  const int nd = (int)L[8], np = (int)L[9];
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= nd * np) return;
+  const T* src = reinterpret_cast<const T*>(static_cast<uintptr_t>(L[10]));
+  const int64_t ssd = L[1], ssp = L[2];
+  int d, p;
+  if (ssd == 1 || ssd == -1) {
+    d = t % nd;
+    p = t / nd;
+  } else {
+    p = t % np;
+    d = t / np;
+  }
+  const int k = blockIdx.y;
+  dst[L[4] + d * L[5] + p * L[6] + k * L[7]] = src[L[0] + d * ssd + p * ssp + k * L[3]];
+}
+
+template <typename T>
+int halo_pull(int nlinks, int nk, int max_strip, const int64_t* links, T* dst, cudaStream_t s) {
+  B2S_ARGCHECK(nlinks >= 0 && nk > 0 && max_strip > 0, "halo_pull: bad sizes nlinks=%d nk=%d max_strip=%d", nlinks, nk, max_strip);
+  if (nlinks == 0) return B2S_OK;
+  B2S_ARGCHECK(links && dst, "halo_pull: null pointer");
+  B2S_ARGCHECK(nk <= 65535 && nlinks <= 65535, "halo_pull: grid too large (nk=%d, nlinks=%d)", nk, nlinks);
+  dim3 grid((max_strip + 255) / 256, nk, nlinks);
+  k_halo_pull<T><<<grid, 256, 0, s>>>(nk, links, dst);
+  return check_launch("halo_pull");
+}
+
+template int halo_pull<double>(int, int, int, const int64_t*, double*, cudaStream_t);
+template int halo_pull<float>(int, int, int, const int64_t*, float*, cudaStream_t);
+
+template int halo_move<double>(int, int, int, const int64_t*, const double*, double*, cudaStream_t);
+template int halo_move<float>(int, int, int, const int64_t*, const float*, float*, cudaStream_t);
 
 }  // namespace impl
 }  // namespace b2s

@@ -21,7 +21,9 @@ static int g_sms = 0;
 static std::mutex g_mu;
 static std::map<std::string, int> g_options = {
     {"fv_variant", 0},      // 0 auto, 1 direct (L1/L2) kernel, 2 TMA-pipelined kernel
-    {"fv_tile", 0},         // TMA tile geometry (k_fv_tma.cu)
+    {"fv_ti", 0},           // TMA tile width: 0 auto, 32 | 64 | 96 | 128 | 192 (k_fv_tma.cu)
+    {"fv_rows", 0},         // rows per stage: 0 auto, 4 | 8
+    {"fv_stages", 0},       // mbarrier ring depth: 0 auto, 2 | 3
 };
 
 int set_error(int code, const char* fmt, ...) {

@@ -6,7 +6,7 @@ import torch
 from b200stencil.halo.partitioner import CubedSpherePartitioner, expected_halo, global_id_field
 
 
-def cpu_mover(links: torch.Tensor, nk: int, src: torch.Tensor, dst: torch.Tensor) -> None:
+def cpu_mover(links: torch.Tensor, nk: int, src: torch.Tensor, dst: torch.Tensor, max_strip: int = 0) -> None:
     """dst[doff + d*dsd + p*dsp + k*dsk] = src[soff + d*ssd + p*ssp + k*ssk] for every link."""
     for L in links.tolist():
         soff, ssd, ssp, ssk, doff, dsd, dsp, dsk, nd, np_ = L

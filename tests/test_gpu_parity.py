@@ -215,6 +215,30 @@ def test_fv_tp2d(st, corc, shape, dtype, variant):
     _fv_case(st, corc, *shape, dtype, variant=variant)
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_fv_tp2d_variants_bit_identical(st, dtype):
+    """Direct kernel, every TMA tile geometry: same bits (explicit-rounding arithmetic, csrc/fv_math.cuh)."""
+    from b200stencil import _abi
+
+    ni, nj, nk = 150, 37, 3
+    f = gen.fv_inputs(ni, nj, nk, dtype)
+    d = {k: up(v) for k, v in f.items()}
+    outs = []
+    combos = [(1, 0, 0, 0)] + [(2, ti, r, st) for ti in (32, 64, 96, 128, 192) for r, st in ((4, 2), (8, 3))]
+    for variant, ti, rows, stages in combos:
+        for name, v in (("fv_variant", variant), ("fv_ti", ti), ("fv_rows", rows), ("fv_stages", stages)):
+            _abi.set_option(name, v)
+        try:
+            out = up(np.zeros((ni, nj, nk), dtype))
+            st.fv_tp2d(d["q"], d["crx"], d["xfx"], d["cry"], d["yfx"], d["rarea"], out)
+            outs.append(down(out))
+        finally:
+            for name in ("fv_variant", "fv_ti", "fv_rows", "fv_stages"):
+                _abi.set_option(name, 0)
+    for o in outs[1:]:
+        assert np.array_equal(o, outs[0])
+
+
 @pytest.mark.parametrize("variant", [0, 1])
 def test_fv_tp2d_regions_and_unaligned(st, corc, variant):
     _fv_case(st, corc, 40, 30, 3, np.float64, variant, region=(3, 37, 3, 27))
