@@ -173,13 +173,22 @@ int saturation_adjust(int ni, int nj, int nk, int nb, F3<const T> p, F3<T> Tt, F
   const bool wide = ni % WMAX == 0 && WidthProbe(WMAX, sizeof(T)).field(p).field(Tt).field(q).field(ql).ok;
   const int W = wide ? WMAX : 1;
   const int ncols = (ni / W) * nj * nb;
-  // pointwise: k is free to be split; keep ~8 levels per thread so 4 fields x 2 levels stay in flight
-  const int kchunk = nk < 8 ? nk : 8;
+  // pointwise: k is free to be split across blockIdx.y
+  int kchunk = option("sat_kchunk", 0);
+  if (kchunk <= 0) kchunk = 4;  // measured best on C180x72 (profiles/): 4 levels per thread, 1 level per load batch
+  if (kchunk > nk) kchunk = nk;
   dim3 grid((ncols + kBlock - 1) / kBlock, (nk + kchunk - 1) / kchunk);
-  if (wide)
-    k_saturation_adjust<T, WMAX, 2><<<grid, kBlock, 0, s>>>(ni / W, nj, nk, ncols, kchunk, p, Tt, q, ql);
-  else
+  const int unroll = option("sat_unroll", 0);
+  if (wide) {
+    if (unroll == 2)
+      k_saturation_adjust<T, WMAX, 2><<<grid, kBlock, 0, s>>>(ni / W, nj, nk, ncols, kchunk, p, Tt, q, ql);
+    else if (unroll == 4)
+      k_saturation_adjust<T, WMAX, 4><<<grid, kBlock, 0, s>>>(ni / W, nj, nk, ncols, kchunk, p, Tt, q, ql);
+    else
+      k_saturation_adjust<T, WMAX, 1><<<grid, kBlock, 0, s>>>(ni / W, nj, nk, ncols, kchunk, p, Tt, q, ql);
+  } else {
     k_saturation_adjust<T, 1, 4><<<grid, kBlock, 0, s>>>(ni, nj, nk, ncols, kchunk, p, Tt, q, ql);
+  }
   return check_launch("saturation_adjust");
 }
 

@@ -119,8 +119,13 @@ int while_in_function(int ni, int nj, int nk, int nb, T threshold, F3<const T> i
         <<<(ncols + kBlock - 1) / kBlock, kBlock, 0, s>>>(ni / WMAX, nj, nk, ncols, threshold, in_field, out_field, cnt);
   } else {
     const int ncols = ni * nj * nb;
-    k_while_in_function<T, 1, 12>
-        <<<(ncols + kBlock - 1) / kBlock, kBlock, 0, s>>>(ni, nj, nk, ncols, threshold, in_field, out_field, cnt);
+    // thin grids (C96: 55k columns, a fraction of one wave) are latency-bound: 24 levels in flight per thread
+    if ((int64_t)ncols < (int64_t)sm_count() * 1024)
+      k_while_in_function<T, 1, 24>
+          <<<(ncols + kBlock - 1) / kBlock, kBlock, 0, s>>>(ni, nj, nk, ncols, threshold, in_field, out_field, cnt);
+    else
+      k_while_in_function<T, 1, 12>
+          <<<(ncols + kBlock - 1) / kBlock, kBlock, 0, s>>>(ni, nj, nk, ncols, threshold, in_field, out_field, cnt);
   }
   return check_launch("while_in_function");
 }

@@ -70,9 +70,16 @@ int pe_prefix(int ni, int nj, int nk, int nb, T ptop, F3<const T> delp, F3<T> pe
 // pointer advances, so every element of pe1/q1/pe2 is requested once.
 // Bytes/point: 24 R + 8 W.
 // -------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(kBlock) k_remap(int ni, int nj, int nk1, int nk2, int ncols, F3<const T> pe1,
-                                                  F3<const T> q1, F3<const T> pe2, F3<T> q2) {
+// Latency-bound by nature: every load depends on the comparison of the previous one.  Variants tried
+// on the device and dropped (profiles/README.md "remap"): a merged-edge uniform loop (no divergence,
+// but twice the steps: issue-bound, 4.7 ms vs 3.5 ms on C720x137), register look-ahead queues of depth
+// 1/2/4/8 (no gain: the extra moves and predicates cost what the overlap wins), per-thread
+// shared-memory rings refilled 4/8/16 levels at a time (slower: lanes refill at different times, so the
+// batched loads lose their coalescing).  What is left is occupancy: 40 registers, 12 CTAs per SM.
+template <typename T, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) k_remap_nested(int ni, int nj, int nk1, int nk2, int ncols,
+                                                         F3<const T> pe1, F3<const T> q1, F3<const T> pe2,
+                                                         F3<T> q2) {
   const int c = blockIdx.x * kBlock + threadIdx.x;
   if (c >= ncols) return;
   const Col cc = decompose_column(c, ni, nj);
@@ -114,7 +121,8 @@ int remap(int ni, int nj, int nk1, int nk2, int nb, F3<const T> pe1, F3<const T>
                nk2, nb);
   B2S_ARGCHECK(pe1.p && q1.p && pe2.p && q2.p, "remap: null field");
   const int ncols = ni * nj * nb;
-  k_remap<T><<<(ncols + kBlock - 1) / kBlock, kBlock, 0, s>>>(ni, nj, nk1, nk2, ncols, pe1, q1, pe2, q2);
+  const int grid = (ncols + kBlock - 1) / kBlock;
+  k_remap_nested<T, 12><<<grid, kBlock, 0, s>>>(ni, nj, nk1, nk2, ncols, pe1, q1, pe2, q2);
   return check_launch("remap");
 }
 

@@ -1,0 +1,109 @@
+"""The C-ABI boundary without a GPU: the generated header is current, the library loads and exports
+every symbol the header declares, the generator follows the reference's schema, errors are loud."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+from b200stencil import _abi
+from b200stencil.bridge import generate
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "b200stencil.h")
+
+
+@pytest.fixture(scope="module")
+def bridge():
+    return generate.Bridge.from_yaml()
+
+
+def test_header_is_generated_from_the_yaml(bridge):
+    with open(HEADER) as f:
+        assert f.read() == bridge.emit_header(), "include/b200stencil.h is stale: run python -m b200stencil.bridge.generate"
+    with open(generate.DEFAULT_GLUE) as f:
+        assert f.read() == bridge.emit_glue()
+
+
+def test_library_exports_every_declared_symbol(bridge):
+    """dlopen works without a device and every prototype of the header resolves (no compute calls)."""
+    assert os.path.exists(_abi.LIB_PATH), "build first: python __graft_entry__.py"
+    lib = ctypes.CDLL(_abi.LIB_PATH)
+    with open(HEADER) as f:
+        declared = re.findall(r"^B2S_API\s+[\w\s\*]+?\b(b2s_\w+)\(", f.read(), flags=re.M)
+    assert len(declared) >= 30 and set(declared) == set(bridge.symbols())
+    for sym in declared:
+        assert hasattr(lib, sym), f"{sym} declared in include/b200stencil.h but not exported"
+    # and nothing else leaks out of the library (visibility=hidden by default)
+    out = subprocess.run(["nm", "-D", "--defined-only", _abi.LIB_PATH], capture_output=True, text=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    assert exported == set(declared)
+
+
+def test_abi_version_and_error_channel_without_gpu():
+    ffi, lib = _abi.load()
+    assert lib.b2s_abi_version() == 1
+    import torch
+
+    if not torch.cuda.is_available():
+        rc = lib.b2s_init(0)
+        assert rc != 0
+        msg = _abi.last_error()
+        assert "no CPU fallback" in msg or "CUDA" in msg
+        with pytest.raises(_abi.B200StencilError):
+            _abi.init(0)
+    assert lib.b2s_set_option(b"fv_variant", 1) == 0 and lib.b2s_get_option(b"fv_variant") == 1
+    assert lib.b2s_set_option(b"fv_variant", 0) == 0
+    assert lib.b2s_set_option(b"no_such_option", 1) == -1
+    with pytest.raises(KeyError):
+        _abi.set_option("no_such_option", 1)
+
+
+def test_schema_follows_the_reference_generator(bridge, tmp_path):
+    """Same YAML keys / argument order / symbol naming as tcn-fpy
+    (/root/reference/src/tcn/py_ftn_interface/argument.py, base.py:35-36, interface.c.jinja2:8)."""
+    fn = bridge.functions["hybrid_index_2dout"]
+    assert [a.name for a in fn.arguments] == ["ni", "nj", "nk", "nb", "data_field", "k_mask", "k_index_desired", "out_field"]
+    assert fn.symbol("b2s", "double") == "b2s_hybrid_index_2dout_c"
+    assert fn.symbol("b2s", "float") == "b2s_hybrid_index_2dout_f32_c"
+    proto = fn.c_prototype("b2s", "float")
+    assert "const float* data_field, int64_t data_field_sj, int64_t data_field_sk, int64_t data_field_sb" in proto
+    assert "float* out_field, int64_t out_field_sj, int64_t out_field_sb, void* stream" in proto
+    assert generate.Argument("is", "int").name_sanitize == "_is"  # reserved names, argument.py:17-20
+    # the reference's own test definition parses with this loader (MPI argument, 'arguments: None')
+    y = tmp_path / "ref.yaml"
+    y.write_text(
+        "type: py_ftn_interface\nname: py_ftn_test\nbridge:\n"
+        "    - name: check_mpi_translation\n      arguments:\n        inputs:\n"
+        "            - !Argument\n              name: comm\n              type: MPI\n"
+        "    - name: check_data\n      arguments:\n        inputs:\n"
+        "            - !Argument\n              name: scalar\n              type: int\n"
+        "            - !Argument\n              name: in_array\n              type: array_float\n              dims: 2\n"
+        "        outputs:\n            - !Argument\n              name: out_array\n              type: array_float\n              dims: 2\n"
+        "    - name: check_empty_function\n      arguments: None\n"
+    )
+    ref = generate.Bridge.from_yaml(str(y))
+    assert list(ref.functions) == ["check_mpi_translation", "check_data", "check_empty_function"]
+    assert ref.functions["check_data"].c_prototype("py_ftn_test", "double").startswith("int py_ftn_test_check_data_c(int scalar, const float* in_array")
+    assert ref.functions["check_empty_function"].arguments == []
+    with pytest.raises(RuntimeError):
+        bad = tmp_path / "bad.yaml"
+        bad.write_text("type: something_else\nname: x\nbridge: []\n")
+        generate.Bridge.from_yaml(str(bad))
+
+
+def test_fortran_interface_module(bridge):
+    f90 = bridge.emit_fortran()
+    assert "module b2s_interface_mod" in f90 and "end module b2s_interface_mod" in f90
+    assert "bind(c, name='b2s_fv_tp2d_c')" in f90 and "bind(c, name='b2s_fv_tp2d_f32_c')" in f90
+    assert f90.count("function b2s_") == 2 * len(bridge.prototypes())  # function ... end function
+    assert "integer(kind=c_int) :: status" in f90
+
+
+def test_missing_library_is_loud(monkeypatch, tmp_path):
+    monkeypatch.setattr(_abi, "LIB_PATH", str(tmp_path / "nope.so"))
+    monkeypatch.setattr(_abi, "_state", {})
+    with pytest.raises(_abi.LibraryMissing) as e:
+        _abi.load()
+    assert "no CPU fallback" in str(e.value)
