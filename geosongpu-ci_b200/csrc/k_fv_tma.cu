@@ -478,7 +478,9 @@ int fv_tp2d_tma(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j1, 
       }
     }
   }
-  if (rows == 0) rows = sizeof(T) == 8 ? 4 : 8;
+  // fp64: 4-row stages (3 CTAs/SM) win on C384-sized sub-domains, 8-row stages (apron re-read 1.75x
+  // instead of 2.5x) on anything larger than ~512^2 (C720x137: 3.85 ms vs 4.17 ms); fp32: always 8.
+  if (rows == 0) rows = (sizeof(T) == 8 && (int64_t)w * (j1 - j0) <= 512 * 512) ? 4 : 8;
   if (stages == 0) stages = 2;
   switch (ti) {
     case 32:
