@@ -160,6 +160,9 @@ def main(argv=None) -> int:
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--dtype", choices=["f64", "f32"], default="f64")
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--workload", choices=["fv", "chain"], default="fv",
+                    help="fv (default, the contract line): fv_tp2d transport step on C384x72; chain: BASELINE configs[4], "
+                         "fv_tp2d + pe_prefix + remap on C720x137 (a separate report, see run_chain)")
     ap.add_argument("--no-overlap", action="store_true", help="exchange, then compute (no interior/frame split)")
     ap.add_argument("--halo", choices=["auto", "p2p", "nccl"], default="auto",
                     help="multi-GPU halo exchange: p2p = device barrier + one peer-memory pull kernel over NVLink "
@@ -173,6 +176,8 @@ def main(argv=None) -> int:
     ns = ap.parse_args(argv)
     if ns.impl == "reference":
         return run_reference(ns)
+    if ns.workload == "chain":
+        return run_chain(ns)
 
     import torch
     import torch.distributed as dist
@@ -444,6 +449,116 @@ def main(argv=None) -> int:
         dist.barrier()
         sys.stdout.flush()
         sys.stderr.flush()
+        os._exit(0)
+    return 0
+
+
+def run_chain(ns) -> int:
+    """BASELINE configs[4]: combined dycore-step chain (horizontal FV + vertical remap scan) on C720x137.
+
+    Not the contract line (that is the C384x72 transport step): prints one JSON line with the same timing
+    protocol (barrier + sync, CUDA events, max over ranks) and the unfused algorithmic byte count 96.1 B/pt.
+    """
+    import torch
+    import torch.distributed as dist
+
+    from b200stencil import fields, stencils
+    from b200stencil.bench import harness
+    from b200stencil.halo.partitioner import CubedSpherePartitioner, layout_for
+    from b200stencil.halo.transport import DycoreChain, FvTransport
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n, nk = 720, 137
+    dtype = torch.float64 if ns.dtype == "f64" else torch.float32
+    es = 8 if ns.dtype == "f64" else 4
+    part = CubedSpherePartitioner(n, layout_for(world), HALO)
+    nsub, ni, nj = part.subdomains_per_gpu(world), part.nx, part.ny
+    g = torch.Generator(device=dev)
+    g.manual_seed(20240724 + 5 + 1000 * rank)
+    mk = lambda s, lo, hi: fields.empty(s, dtype, dev, batch=nsub).uniform_(lo, hi, generator=g)  # noqa: E731
+    exchange, sym_q = "nccl", None
+    if world > 1:
+        from b200stencil.halo.p2p import SymmetricField
+
+        sym_q = SymmetricField((ni + 6, nj + 6, nk), nsub, dtype, dev)
+        exchange = "p2p"
+        q = sym_q.field.uniform_(0.5, 1.5, generator=g)
+    else:
+        q = mk((ni + 6, nj + 6, nk), 0.5, 1.5)
+    crx, cry = mk((ni + 1, nj, nk), -0.9, 0.9), mk((ni, nj + 1, nk), -0.9, 0.9)
+    xfx = mk((ni + 1, nj, nk), 0.9, 1.1).mul_(crx)
+    yfx = mk((ni, nj + 1, nk), 0.9, 1.1).mul_(cry)
+    rarea = mk((ni, nj), 0.9, 1.1)
+    delp = mk((ni, nj, nk), 0.5e5 / nk, 1.5e5 / nk)
+    pe1 = fields.empty((ni, nj, nk + 1), dtype, dev, batch=nsub)
+    stencils.pe_prefix(delp, 1.0, pe1)
+    sig = (torch.arange(nk + 1, device=dev, dtype=torch.float64) / nk).to(dtype)
+    pe2 = fields.empty((ni, nj, nk + 1), dtype, dev, batch=nsub)
+    pe2[...] = pe1[..., :1] + (pe1[..., -1:] - pe1[..., :1]) * sig
+    pe2[..., -1] = pe1[..., -1]
+    q_adv = fields.empty((ni, nj, nk), dtype, dev, batch=nsub)
+    q_new = fields.empty((ni, nj, nk), dtype, dev, batch=nsub)
+    chain = DycoreChain(FvTransport(part, world, rank, overlap=False, exchange=exchange, symmetric_q=sym_q))
+    args = (q, crx, xfx, cry, yfx, rarea, delp, pe2, q_adv, pe1, q_new)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, ns.warmup)):
+        chain.step(*args)
+    barrier()
+    graph = None
+    if world > 1 and not ns.no_graph:
+        cap = torch.cuda.Stream(device=dev)
+        cap.wait_stream(torch.cuda.current_stream(dev))
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=cap):
+            chain.step(*args)
+        graph.replay()
+        barrier()
+    K = ns.steps
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        graph.replay() if graph is not None else chain.step(*args)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    total_points = 6 * n * n * nk
+    bpp = (6 * es + es / nk) + 2 * es + 4 * es
+    peaks = harness.measured_peaks(ROOT)
+    if rank == 0:
+        gbs = total_points / world * bpp / (ms / K * 1e-3) / 1e9
+        print(json.dumps({
+            "metric": "grid-cells x levels per second, dycore chain fv_tp2d + pe_prefix + remap (C720x137, 6 tiles)",
+            "value": total_points * K / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(3, ns.warmup),
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": ns.dtype,
+            "data": "synthetic",
+            "config": {"workload": "dycore chain on C720x137 (BASELINE configs[4])", "subdomains_per_gpu": nsub,
+                       "subdomain": [ni, nj], "halo_exchange": exchange if world > 1 else "local",
+                       "launch": "cuda-graph replay" if graph is not None else "eager launches"},
+            "roofline": {"bound": "hbm", "achieved": round(gbs, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": round(gbs / peaks["hbm_gbs"], 4), "traffic": None,
+                         "kernel": "whole chain (unfused algorithmic bytes 96.1 B/pt in fp64), per GPU"},
+        }), flush=True)  # fmt: skip
+    if world > 1:
+        graph = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
         os._exit(0)
     return 0
 

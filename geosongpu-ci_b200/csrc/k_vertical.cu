@@ -70,12 +70,15 @@ int pe_prefix(int ni, int nj, int nk, int nb, T ptop, F3<const T> delp, F3<T> pe
 // pointer advances, so every element of pe1/q1/pe2 is requested once.
 // Bytes/point: 24 R + 8 W.
 // -------------------------------------------------------------------------------------------
-// Latency-bound by nature: every load depends on the comparison of the previous one.  Variants tried
-// on the device and dropped (profiles/README.md "remap"): a merged-edge uniform loop (no divergence,
-// but twice the steps: issue-bound, 4.7 ms vs 3.5 ms on C720x137), register look-ahead queues of depth
-// 1/2/4/8 (no gain: the extra moves and predicates cost what the overlap wins), per-thread
-// shared-memory rings refilled 4/8/16 levels at a time (slower: lanes refill at different times, so the
-// batched loads lose their coalescing).  What is left is occupancy: 40 registers, 12 CTAs per SM.
+// Latency-bound by nature: every load depends on the comparison of the previous one (ncu source page:
+// 39 % of warp samples wait for the source edge the preceding advance loaded, 30 % for the target edge
+// loaded at the top of the level).  What hides that latency here is plain occupancy: ~45 registers,
+// 10-11 CTAs (40+ warps) per SM.  Every restructuring tried on the device LOST to this kernel
+// (3.5-3.8 ms on C720x137 fp64; profiles/README.md "remap"): a merged-edge uniform loop (4.7 ms),
+// register look-ahead queues of depth 1/2/4/8 (3.5-6.0 ms), per-thread shared-memory rings refilled at
+// lane-specific times (5.2-16 ms), rings refilled at uniform points per thread (5.4-6.8 ms) or anchored
+// at the slowest lane of the warp (4.8-5.2 ms): each adds instructions and registers (fewer resident
+// warps) faster than it removes stalls.
 template <typename T, int MINB>
 __global__ void __launch_bounds__(kBlock, MINB) k_remap_nested(int ni, int nj, int nk1, int nk2, int ncols,
                                                          F3<const T> pe1, F3<const T> q1, F3<const T> pe2,
@@ -83,33 +86,43 @@ __global__ void __launch_bounds__(kBlock, MINB) k_remap_nested(int ni, int nj, i
   const int c = blockIdx.x * kBlock + threadIdx.x;
   if (c >= ncols) return;
   const Col cc = decompose_column(c, ni, nj);
-  const T* e1 = pe1.at(cc.i, cc.j, 0, cc.b);
-  const T* s1 = q1.at(cc.i, cc.j, 0, cc.b);
-  const T* e2 = pe2.at(cc.i, cc.j, 0, cc.b);
-  T* o2 = q2.at(cc.i, cc.j, 0, cc.b);
+  // running pointers, bumped by one level per advance: the kernel is issue-bound (profiles/README.md),
+  // and a 64-bit multiply per address costs more instructions than the arithmetic of a layer
+  const T* pb = pe1.at(cc.i, cc.j, 1, cc.b);  // -> pe1[k1 + 1]
+  const T* pq = q1.at(cc.i, cc.j, 0, cc.b);   // -> q1[k1]
+  const T* pt = pe2.at(cc.i, cc.j, 0, cc.b);  // -> pe2[k2]
+  T* po = q2.at(cc.i, cc.j, 0, cc.b);         // -> q2[k2]
+  const int64_t e_sk = pe1.sk, q_sk = q1.sk, t_sk = pe2.sk, o_sk = q2.sk;
   int k1 = 0;
-  T top = __ldg(e1), bot = __ldg(e1 + pe1.sk), qv = __ldg(s1);
-  T lo = __ldg(e2);
+  const int last = nk1 - 1;
+  T top = __ldg(pb - e_sk), bot = __ldg(pb), qv = __ldg(pq);
+  T lo = __ldg(pt);
   for (int k2 = 0; k2 < nk2; ++k2) {
-    const T hi = __ldg(e2 + (int64_t)(k2 + 1) * pe2.sk);
-    while (k1 < nk1 - 1 && bot <= lo) {
+    pt += t_sk;
+    const T hi = __ldg(pt);
+    while (k1 < last && bot <= lo) {
       ++k1;
+      pb += e_sk;
+      pq += q_sk;
       top = bot;
-      bot = __ldg(e1 + (int64_t)(k1 + 1) * pe1.sk);
-      qv = __ldg(s1 + (int64_t)k1 * q1.sk);
+      bot = __ldg(pb);
+      qv = __ldg(pq);
     }
     T acc = T(0);
     for (;;) {
       const T a = lo > top ? lo : top;
       const T b = hi < bot ? hi : bot;
       if (b > a) acc = acc + (b - a) * qv;
-      if (bot >= hi || k1 == nk1 - 1) break;
+      if (bot >= hi || k1 == last) break;
       ++k1;
+      pb += e_sk;
+      pq += q_sk;
       top = bot;
-      bot = __ldg(e1 + (int64_t)(k1 + 1) * pe1.sk);
-      qv = __ldg(s1 + (int64_t)k1 * q1.sk);
+      bot = __ldg(pb);
+      qv = __ldg(pq);
     }
-    __stcs(o2 + (int64_t)k2 * q2.sk, acc / (hi - lo));
+    __stcs(po, acc / (hi - lo));
+    po += o_sk;
     lo = hi;
   }
 }
@@ -122,7 +135,7 @@ int remap(int ni, int nj, int nk1, int nk2, int nb, F3<const T> pe1, F3<const T>
   B2S_ARGCHECK(pe1.p && q1.p && pe2.p && q2.p, "remap: null field");
   const int ncols = ni * nj * nb;
   const int grid = (ncols + kBlock - 1) / kBlock;
-  k_remap_nested<T, 12><<<grid, kBlock, 0, s>>>(ni, nj, nk1, nk2, ncols, pe1, q1, pe2, q2);
+  k_remap_nested<T, 10><<<grid, kBlock, 0, s>>>(ni, nj, nk1, nk2, ncols, pe1, q1, pe2, q2);
   return check_launch("remap");
 }
 

@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -x -q -k "vertical" 2>&1 | tail -3
+timeout 600 python -m pytest tests -m gpu -x -q -k "vertical or chain" 2>&1 | tail -3
 cd geosongpu-ci_b200
 show() { python -c "
 import sys,json
@@ -10,4 +10,4 @@ for line in sys.stdin:
     else: print(line[:300])
 "; }
 echo "== remap variants"
-for v in 0 208 216 12; do timeout 100 python -m b200stencil.bench.sweep --stencils remap --iters 5 --option remap_variant=$v 2>&1 | tail -2 | show; done
+for v in 0 2 3 1; do timeout 100 python -m b200stencil.bench.sweep --stencils remap --iters 5 --option remap_variant=$v 2>&1 | tail -2 | show; done
