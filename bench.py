@@ -170,6 +170,8 @@ def main(argv=None) -> int:
                          "interior; auto = p2p when it can be set up, else nccl")
     ap.add_argument("--graph", action="store_true", help="replay the step from a CUDA graph (default when --gpus > 1)")
     ap.add_argument("--no-graph", action="store_true", help="always launch eagerly")
+    ap.add_argument("--fused-remap", action="store_true", help="[chain] fold pe_prefix into the remap kernel (remap_delp)")
+    ap.add_argument("--hws-dump", default=None, help="write the hws sampler record of the run (npz) to this path")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--skip-e2e", action="store_true")
@@ -346,12 +348,28 @@ def main(argv=None) -> int:
         kernel_ms = statistics.median(a.elapsed_time(b) for a, b in k_events[:60])
     else:
         kernel_ms = statistics.median(a.elapsed_time(b) for a, b in k_events)
+    hws_summary = None
     if sampler is not None:
         time.sleep(0.05)
         sampler.stop()
         clocks = sampler.clocks_summary(local_rank, since=t_wall0, until=t_wall1 + 0.05)
         if not clocks["samples"]:
             clocks = sampler.clocks_summary(local_rank)
+        # the repo's hardware sampler (b200stencil.hws, successor of tcn.hws): every visible GPU, 50 Hz
+        d = sampler.dump_dict()
+        sel = [i for i, t in enumerate(d["timestamps"]) if t_wall0 <= t <= t_wall1 + 0.05] or list(range(len(d["timestamps"])))
+        if sel:
+            ng = len(d["gpu_indices"])
+            hws_summary = {
+                "samples": len(sel), "dt_s": sampler.dt, "gpus": ng,
+                "gpu_power_w_mean": [round(sum(d["gpu_psu"][i][g] for i in sel) / len(sel), 1) for g in range(ng)],
+                "gpu_util_pct_mean": [round(sum(d["gpu_exe_utl"][i][g] for i in sel) / len(sel), 1) for g in range(ng)],
+                "gpu_mem_used_mib_max": [round(max(d["gpu_mem"][i][g] for i in sel)) for g in range(ng)],
+            }  # fmt: skip
+        if ns.hws_dump:
+            from b200stencil.hws import server as hws_server
+
+            hws_server.dump(sampler, os.path.splitext(ns.hws_dump)[0], "npz")
     else:
         clocks = {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable: NVML sampler failed to start"]}
 
@@ -435,7 +453,7 @@ def main(argv=None) -> int:
                 "halo_bytes_over_nvlink_per_gpu_per_step": (tr.p2p.remote_bytes if tr.p2p is not None
                                                             else tr.updater.bytes_sent_per_update),
             },
-            "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches),
+            "roofline": roofline, "clocks": clocks, "hws": hws_summary, "gpu_launches": int(launches),
             "e2e": e2e, "cpu_baseline": cpu,
         }  # fmt: skip
         if cpu_numpy is not None:
@@ -504,7 +522,8 @@ def run_chain(ns) -> int:
     pe2[..., -1] = pe1[..., -1]
     q_adv = fields.empty((ni, nj, nk), dtype, dev, batch=nsub)
     q_new = fields.empty((ni, nj, nk), dtype, dev, batch=nsub)
-    chain = DycoreChain(FvTransport(part, world, rank, overlap=False, exchange=exchange, symmetric_q=sym_q))
+    chain = DycoreChain(FvTransport(part, world, rank, overlap=False, exchange=exchange, symmetric_q=sym_q),
+                        fused=ns.fused_remap)
     args = (q, crx, xfx, cry, yfx, rarea, delp, pe2, q_adv, pe1, q_new)
 
     def barrier():
@@ -549,7 +568,8 @@ def run_chain(ns) -> int:
             "data": "synthetic",
             "config": {"workload": "dycore chain on C720x137 (BASELINE configs[4])", "subdomains_per_gpu": nsub,
                        "subdomain": [ni, nj], "halo_exchange": exchange if world > 1 else "local",
-                       "launch": "cuda-graph replay" if graph is not None else "eager launches"},
+                       "launch": "cuda-graph replay" if graph is not None else "eager launches",
+                       "vertical": "remap_delp (pe_prefix fused into remap)" if ns.fused_remap else "pe_prefix + remap"},
             "roofline": {"bound": "hbm", "achieved": round(gbs, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": round(gbs / peaks["hbm_gbs"], 4), "traffic": None,
                          "kernel": "whole chain (unfused algorithmic bytes 96.1 B/pt in fp64), per GPU"},

@@ -96,9 +96,11 @@ class DycoreChain:
     Algorithmic bytes/point (fp64): 48.1 + 16 + 32 = 96.1.
     """
 
-    def __init__(self, transport: FvTransport, ptop: float = 1.0):
+    def __init__(self, transport: FvTransport, ptop: float = 1.0, fused: bool = False):
+        """``fused``: use ``remap_delp`` (pe_prefix folded into the remap; pe1 is then not written)."""
         self.transport = transport
         self.ptop = float(ptop)
+        self.fused = fused
         self._calls = {}
 
     def step(self, q, crx, xfx, cry, yfx, rarea, delp, pe2, q_adv, pe1, q_new) -> None:
@@ -110,11 +112,19 @@ class DycoreChain:
             ni, nj, nk, nb = shape3(delp)
             nk2 = shape3(q_new)[2]
             prec = _abi.precision_of(delp)
-            self._calls[key] = (
-                _abi.prepare("pe_prefix", prec, dict(ni=ni, nj=nj, nk=nk, nb=nb, ptop=self.ptop, delp=delp, pe=pe1)),
-                _abi.prepare("remap", prec, dict(ni=ni, nj=nj, nk1=nk, nk2=nk2, nb=nb, pe1=pe1, q1=q_adv, pe2=pe2, q2=q_new)),
-            )
+            if self.fused:
+                self._calls[key] = (
+                    None,
+                    _abi.prepare("remap_delp", prec, dict(ni=ni, nj=nj, nk1=nk, nk2=nk2, nb=nb, ptop=self.ptop,
+                                                          delp=delp, q1=q_adv, pe2=pe2, q2=q_new)),
+                )  # fmt: skip
+            else:
+                self._calls[key] = (
+                    _abi.prepare("pe_prefix", prec, dict(ni=ni, nj=nj, nk=nk, nb=nb, ptop=self.ptop, delp=delp, pe=pe1)),
+                    _abi.prepare("remap", prec, dict(ni=ni, nj=nj, nk1=nk, nk2=nk2, nb=nb, pe1=pe1, q1=q_adv, pe2=pe2, q2=q_new)),
+                )  # fmt: skip
         pe_prefix, remap = self._calls[key]
         self.transport.step(q, crx, xfx, cry, yfx, rarea, q_adv)
-        pe_prefix()
+        if pe_prefix is not None:
+            pe_prefix()
         remap()

@@ -26,7 +26,7 @@ async def _sample_loop(sampler: Sampler, dt: float):
 def dump(sampler: Sampler, name: str, fmt: str = HWS_DUMP_FORMAT) -> str:
     d = sampler.dump_dict()
     if fmt == HWS_DUMP_NPZ:
-        path = f"./{name}.npz"
+        path = f"{name}.npz"
         np.savez_compressed(path, **{k: np.asarray(v) for k, v in d.items()})
     elif fmt == HWS_DUMP_JSON:
         path = f"{name}.json"

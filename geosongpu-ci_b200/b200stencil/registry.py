@@ -106,6 +106,7 @@ def _install_builtin() -> None:
     register("fv_tp2d", stencils.fv_tp2d)
     register("pe_prefix", stencils.pe_prefix)
     register("remap", stencils.remap)
+    register("remap_delp", stencils.remap_delp)
     register("tridiag", stencils.tridiag)
 
 

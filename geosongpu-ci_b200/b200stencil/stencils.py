@@ -113,6 +113,17 @@ def remap(pe1, q1, pe2, q2, stream=None) -> None:
     _abi.call("remap", _abi.precision_of(q1), dict(ni=ni, nj=nj, nk1=nk1, nk2=nk2, nb=nb, pe1=pe1, q1=q1, pe2=pe2, q2=q2), stream)
 
 
+def remap_delp(delp, ptop: float, q1, pe2, q2, stream=None) -> None:
+    """pe_prefix fused into remap (csrc/k_vertical.cu k_remap_delp): bit-identical to
+    ``pe_prefix(delp, ptop, pe1); remap(pe1, q1, pe2, q2)`` without materialising pe1."""
+    ni, nj, nk1, nb = shape3(q1)
+    nk2 = shape3(q2)[2]
+    _abi.call(
+        "remap_delp", _abi.precision_of(q1),
+        dict(ni=ni, nj=nj, nk1=nk1, nk2=nk2, nb=nb, ptop=float(ptop), delp=delp, q1=q1, pe2=pe2, q2=q2), stream,
+    )  # fmt: skip
+
+
 def tridiag(a, b, c, d, x, w=None, stream=None) -> None:
     """S6c (spec: oracle/numpy_oracle.py tridiag) -- K6c; ``w`` is scratch shaped like ``x``."""
     ni, nj, nk, nb = shape3(b)

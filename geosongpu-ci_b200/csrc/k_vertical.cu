@@ -86,43 +86,35 @@ __global__ void __launch_bounds__(kBlock, MINB) k_remap_nested(int ni, int nj, i
   const int c = blockIdx.x * kBlock + threadIdx.x;
   if (c >= ncols) return;
   const Col cc = decompose_column(c, ni, nj);
-  // running pointers, bumped by one level per advance: the kernel is issue-bound (profiles/README.md),
-  // and a 64-bit multiply per address costs more instructions than the arithmetic of a layer
-  const T* pb = pe1.at(cc.i, cc.j, 1, cc.b);  // -> pe1[k1 + 1]
-  const T* pq = q1.at(cc.i, cc.j, 0, cc.b);   // -> q1[k1]
-  const T* pt = pe2.at(cc.i, cc.j, 0, cc.b);  // -> pe2[k2]
-  T* po = q2.at(cc.i, cc.j, 0, cc.b);         // -> q2[k2]
-  const int64_t e_sk = pe1.sk, q_sk = q1.sk, t_sk = pe2.sk, o_sk = q2.sk;
+  // (running pointers bumped per advance instead of the index arithmetic below measured 9 % SLOWER on
+  //  C720x137 -- 3.81 ms vs 3.49 ms, three runs each -- so the indices stay)
+  const T* e1 = pe1.at(cc.i, cc.j, 0, cc.b);
+  const T* s1 = q1.at(cc.i, cc.j, 0, cc.b);
+  const T* e2 = pe2.at(cc.i, cc.j, 0, cc.b);
+  T* o2 = q2.at(cc.i, cc.j, 0, cc.b);
   int k1 = 0;
-  const int last = nk1 - 1;
-  T top = __ldg(pb - e_sk), bot = __ldg(pb), qv = __ldg(pq);
-  T lo = __ldg(pt);
+  T top = __ldg(e1), bot = __ldg(e1 + pe1.sk), qv = __ldg(s1);
+  T lo = __ldg(e2);
   for (int k2 = 0; k2 < nk2; ++k2) {
-    pt += t_sk;
-    const T hi = __ldg(pt);
-    while (k1 < last && bot <= lo) {
+    const T hi = __ldg(e2 + (int64_t)(k2 + 1) * pe2.sk);
+    while (k1 < nk1 - 1 && bot <= lo) {
       ++k1;
-      pb += e_sk;
-      pq += q_sk;
       top = bot;
-      bot = __ldg(pb);
-      qv = __ldg(pq);
+      bot = __ldg(e1 + (int64_t)(k1 + 1) * pe1.sk);
+      qv = __ldg(s1 + (int64_t)k1 * q1.sk);
     }
     T acc = T(0);
     for (;;) {
       const T a = lo > top ? lo : top;
       const T b = hi < bot ? hi : bot;
       if (b > a) acc = acc + (b - a) * qv;
-      if (bot >= hi || k1 == last) break;
+      if (bot >= hi || k1 == nk1 - 1) break;
       ++k1;
-      pb += e_sk;
-      pq += q_sk;
       top = bot;
-      bot = __ldg(pb);
-      qv = __ldg(pq);
+      bot = __ldg(e1 + (int64_t)(k1 + 1) * pe1.sk);
+      qv = __ldg(s1 + (int64_t)k1 * q1.sk);
     }
-    __stcs(po, acc / (hi - lo));
-    po += o_sk;
+    __stcs(o2 + (int64_t)k2 * q2.sk, acc / (hi - lo));
     lo = hi;
   }
 }
@@ -135,8 +127,64 @@ int remap(int ni, int nj, int nk1, int nk2, int nb, F3<const T> pe1, F3<const T>
   B2S_ARGCHECK(pe1.p && q1.p && pe2.p && q2.p, "remap: null field");
   const int ncols = ni * nj * nb;
   const int grid = (ncols + kBlock - 1) / kBlock;
-  k_remap_nested<T, 10><<<grid, kBlock, 0, s>>>(ni, nj, nk1, nk2, ncols, pe1, q1, pe2, q2);
+  k_remap_nested<T, 12><<<grid, kBlock, 0, s>>>(ni, nj, nk1, nk2, ncols, pe1, q1, pe2, q2);
   return check_launch("remap");
+}
+
+// -------------------------------------------------------------------------------------------
+// K6a+b fused, remap_delp: the source edges of the remap ARE the prefix sum of delp
+// (pe1[k+1] = pe1[k] + delp[k], pe1[0] = ptop), so the marching pointer builds them as it goes:
+// same additions in the same order as pe_prefix, same overlaps as remap -> bit-identical to running
+// the two kernels, without writing pe1 (8 B/pt) or reading it back (8 B/pt), and one launch fewer.
+// Bytes/point: 24 R (delp, q1, pe2) + 8 W; the unfused pair moves 48.
+// -------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kBlock, 12) k_remap_delp(int ni, int nj, int nk1, int nk2, int ncols, T ptop,
+                                                           F3<const T> delp, F3<const T> q1, F3<const T> pe2,
+                                                           F3<T> q2) {
+  const int c = blockIdx.x * kBlock + threadIdx.x;
+  if (c >= ncols) return;
+  const Col cc = decompose_column(c, ni, nj);
+  const T* d1 = delp.at(cc.i, cc.j, 0, cc.b);
+  const T* s1 = q1.at(cc.i, cc.j, 0, cc.b);
+  const T* e2 = pe2.at(cc.i, cc.j, 0, cc.b);
+  T* o2 = q2.at(cc.i, cc.j, 0, cc.b);
+  int k1 = 0;
+  T top = ptop, bot = ptop + __ldg(d1), qv = __ldg(s1);
+  T lo = __ldg(e2);
+  for (int k2 = 0; k2 < nk2; ++k2) {
+    const T hi = __ldg(e2 + (int64_t)(k2 + 1) * pe2.sk);
+    while (k1 < nk1 - 1 && bot <= lo) {
+      ++k1;
+      top = bot;
+      bot = top + __ldg(d1 + (int64_t)k1 * delp.sk);
+      qv = __ldg(s1 + (int64_t)k1 * q1.sk);
+    }
+    T acc = T(0);
+    for (;;) {
+      const T a = lo > top ? lo : top;
+      const T b = hi < bot ? hi : bot;
+      if (b > a) acc = acc + (b - a) * qv;
+      if (bot >= hi || k1 == nk1 - 1) break;
+      ++k1;
+      top = bot;
+      bot = top + __ldg(d1 + (int64_t)k1 * delp.sk);
+      qv = __ldg(s1 + (int64_t)k1 * q1.sk);
+    }
+    __stcs(o2 + (int64_t)k2 * q2.sk, acc / (hi - lo));
+    lo = hi;
+  }
+}
+
+template <typename T>
+int remap_delp(int ni, int nj, int nk1, int nk2, int nb, T ptop, F3<const T> delp, F3<const T> q1, F3<const T> pe2,
+               F3<T> q2, cudaStream_t s) {
+  B2S_ARGCHECK(ni > 0 && nj > 0 && nk1 > 0 && nk2 > 0 && nb > 0, "remap_delp: empty domain %dx%dx(%d->%d)x%d", ni, nj,
+               nk1, nk2, nb);
+  B2S_ARGCHECK(delp.p && q1.p && pe2.p && q2.p, "remap_delp: null field");
+  const int ncols = ni * nj * nb;
+  k_remap_delp<T><<<(ncols + kBlock - 1) / kBlock, kBlock, 0, s>>>(ni, nj, nk1, nk2, ncols, ptop, delp, q1, pe2, q2);
+  return check_launch("remap_delp");
 }
 
 // -------------------------------------------------------------------------------------------
@@ -220,6 +268,7 @@ int tridiag(int ni, int nj, int nk, int nb, F3<const T> a, F3<const T> b, F3<con
 #define INSTANTIATE(T)                                                                                        \
   template int pe_prefix<T>(int, int, int, int, T, F3<const T>, F3<T>, cudaStream_t);                         \
   template int remap<T>(int, int, int, int, int, F3<const T>, F3<const T>, F3<const T>, F3<T>, cudaStream_t); \
+  template int remap_delp<T>(int, int, int, int, int, T, F3<const T>, F3<const T>, F3<const T>, F3<T>, cudaStream_t); \
   template int tridiag<T>(int, int, int, int, F3<const T>, F3<const T>, F3<const T>, F3<const T>, F3<T>, F3<T>, cudaStream_t);
 INSTANTIATE(double)
 INSTANTIATE(float)

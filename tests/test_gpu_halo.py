@@ -126,6 +126,9 @@ def test_dycore_chain_matches_oracle(dtype):
     q_adv, pe1_d, q_new = F.zeros((N, N, nk), dtype, batch=6), F.zeros((N, N, nk + 1), dtype, batch=6), F.zeros((N, N, nk), dtype, batch=6)
     chain = DycoreChain(FvTransport(part, 1, 0), ptop)
     chain.step(q, d_crx, d_xfx, d_cry, d_yfx, d_rarea, d_delp, d_pe2, q_adv, pe1_d, q_new)
+    q_fused = F.zeros((N, N, nk), dtype, batch=6)
+    DycoreChain(FvTransport(part, 1, 0), ptop, fused=True).step(q, d_crx, d_xfx, d_cry, d_yfx, d_rarea, d_delp, d_pe2, q_adv, pe1_d, q_fused)
+    assert torch.equal(q_fused, q_new), "remap_delp must reproduce pe_prefix + remap bit for bit"
     got = q_new.cpu().numpy()
     rtol = 1e-12 if dtype == torch.float64 else 1e-5
     assert np.all(np.abs(got - ref) <= rtol * np.maximum(np.abs(ref), np.abs(ref).max()))

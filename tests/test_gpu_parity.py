@@ -304,6 +304,11 @@ def test_vertical(st, shape, dtype):
     assert_close(down(q2), ref, RTOL[dtype], "q2")
     assert np.array_equal(down(q2), ref), "remap is compiled without FMA contraction: expected bit-exact"
 
+    # pe_prefix fused into the remap: same bits as the two kernels (and as the oracle)
+    q2f = up(np.zeros((ni, nj, nk2), dtype))
+    st.remap_delp(up(v["delp"]), v["ptop"], up(v["q1"]), up(v["pe2"]), q2f)
+    assert np.array_equal(down(q2f), ref)
+
     t = gen.tridiag_inputs(ni, nj, nk, dtype)
     ref = zeros_like_np(shape, dtype)
     orc.tridiag(t["a"], t["b"], t["c"], t["d"], ref)
