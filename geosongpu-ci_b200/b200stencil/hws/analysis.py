@@ -1,64 +1,71 @@
-"""Energy envelope of an hws dump (reference: /root/reference/src/tcn/hws/analysis.py:20-72).
+"""Energy of a sampled run from an hws dump.
 
-The reference integrates power over SAMPLE INDEX and then guesses the time base from the default
-sample rate (flagged "Wrong?!" by its author, :38-50).  Dumps written here carry timestamps, so the
-integral is taken over time and kWh is exact; the sample-index figures are kept for comparison.
+The reference integrates power over the SAMPLE INDEX and then guesses a time base from the default sample
+rate (its author flags the kWh figure "Wrong?!", /root/reference/src/tcn/hws/analysis.py:27,38-50).  Dumps
+written by this package carry timestamps and ``dt``, so the integral is taken over time and the energy is
+exact; the sample-index integral is still reported (``*_kw_samples``) for comparison with old dumps.
 """
 from __future__ import annotations
 
-import dataclasses
+from dataclasses import dataclass
 from typing import Any, Dict, Optional
 
 import numpy as np
 
+_trapezoid = getattr(np, "trapezoid", None) or np.trapz
 
-@dataclasses.dataclass
+
+@dataclass
 class EnergyReport:
-    CPU_envelop_integrated: float = 0  # kW * sample_count   (reference unit)
-    CPU_envelop_kWh: float = 0
-    GPU_envelop_integrated: float = 0
-    GPU_envelop_kWh: float = 0
-    overall_envelop_integrated: float = 0
-    overall_envelop_kWh: float = 0
-    duration_s: float = 0
-    samples: int = 0
+    samples: int
+    duration_s: float
+    cpu_wh: float
+    gpu_wh: float
+    cpu_kw_samples: float  # reference unit: kW x sample count
+    gpu_kw_samples: float
+
+    @property
+    def total_wh(self) -> float:
+        return self.cpu_wh + self.gpu_wh
+
+    @property
+    def total_kwh(self) -> float:
+        return self.total_wh / 1000.0
+
+    def describe(self) -> str:
+        lines = [
+            f"{self.samples} samples over {self.duration_s:.2f} s",
+            f"  CPU  {self.cpu_wh:10.4f} Wh   ({self.cpu_kw_samples:.2f} kW.samples)",
+            f"  GPU  {self.gpu_wh:10.4f} Wh   ({self.gpu_kw_samples:.2f} kW.samples)",
+            f"  all  {self.total_wh:10.4f} Wh",
+        ]
+        return "\n".join(lines)
 
 
-def _trapz(y, x=None):
-    fn = getattr(np, "trapezoid", None) or np.trapz
-    return float(fn(y, x)) if x is not None else float(fn(y))
-
-
-def energy_envelop_calculation(cpu_psu_data, gpu_psu_data, timestamps: Optional[np.ndarray] = None,
-                               dt: Optional[float] = None, verbose: bool = True) -> EnergyReport:
-    """cpu_psu_data [samples] in W, gpu_psu_data [samples] or [samples, gpus] in W."""
-    cpu = np.asarray(cpu_psu_data, dtype=float)
-    gpu = np.asarray(gpu_psu_data, dtype=float)
+def energy_report(cpu_w, gpu_w, timestamps: Optional[np.ndarray] = None, dt: Optional[float] = None) -> EnergyReport:
+    """cpu_w [samples] and gpu_w [samples] or [samples, gpus] in watts -> energy in Wh."""
+    cpu = np.asarray(cpu_w, dtype=float)
+    gpu = np.asarray(gpu_w, dtype=float)
     if gpu.ndim == 2:
-        gpu = gpu.sum(axis=1)  # all GPUs of the node
-    n = len(cpu)
+        gpu = gpu.sum(axis=1)  # every GPU of the node
+    n = int(cpu.shape[0])
     if timestamps is not None and len(timestamps) == n:
-        t = np.asarray(timestamps, dtype=float) - float(timestamps[0])
+        t = np.asarray(timestamps, dtype=float)
+        t = t - t[0] if n else t
     else:
-        t = np.arange(n) * (dt if dt is not None else 0.1)
-    r = EnergyReport(samples=n, duration_s=float(t[-1]) if n else 0.0)
-    r.GPU_envelop_integrated = _trapz(gpu / 1000)
-    r.CPU_envelop_integrated = _trapz(cpu / 1000)
-    r.overall_envelop_integrated = r.GPU_envelop_integrated + r.CPU_envelop_integrated
-    r.GPU_envelop_kWh = _trapz(gpu / 1000, t) / 3600
-    r.CPU_envelop_kWh = _trapz(cpu / 1000, t) / 3600
-    r.overall_envelop_kWh = r.GPU_envelop_kWh + r.CPU_envelop_kWh
-    if verbose:
-        print(
-            f"Number of samples: {n} over {r.duration_s:.2f} s\n"
-            f"CPU envelop: {r.CPU_envelop_kWh * 1000:.4f} Wh\n"
-            f"GPU envelop: {r.GPU_envelop_kWh * 1000:.4f} Wh\n"
-            f"Overall envelop: {r.overall_envelop_kWh * 1000:.4f} Wh"
-        )
-    return r
+        t = np.arange(n) * (0.1 if dt is None else dt)
+    joule = lambda w: float(_trapezoid(w, t)) if n > 1 else 0.0  # noqa: E731
+    return EnergyReport(
+        samples=n,
+        duration_s=float(t[-1]) if n else 0.0,
+        cpu_wh=joule(cpu) / 3600.0,
+        gpu_wh=joule(gpu) / 3600.0,
+        cpu_kw_samples=float(_trapezoid(cpu / 1000.0)) if n > 1 else 0.0,
+        gpu_kw_samples=float(_trapezoid(gpu / 1000.0)) if n > 1 else 0.0,
+    )
 
 
-def load_data(data_filepath: str, data_format: str = "npz") -> Dict[str, Any]:
-    if data_format != "npz":
-        raise NotImplementedError(f"Format {data_format} not implemented")
-    return np.load(data_filepath, allow_pickle=False)
+def load(path: str) -> Dict[str, Any]:
+    if not path.endswith(".npz"):
+        raise NotImplementedError("only npz dumps can be analysed")
+    return dict(np.load(path, allow_pickle=False))

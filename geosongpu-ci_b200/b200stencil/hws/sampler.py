@@ -15,7 +15,8 @@ import threading
 import time
 from typing import Dict, List, Optional, Sequence
 
-from .constants import HWS_HARDWARE_SPECS, HWS_HW_CPU, SERIES_CPU, SERIES_GPU
+from .protocol import SERIES_CPU, SERIES_GPU
+from .specs import CPU_LABEL, cpu_power_w
 
 # nvmlClocksEventReasons bits (nvml.h)
 REASON_BITS = {
@@ -110,7 +111,7 @@ class Sampler:
     """Collects samples from a provider; usable as a background thread (``start``/``stop``) or
     driven externally (``sample_once``, used by the asyncio server)."""
 
-    def __init__(self, provider=None, dt: float = 0.1, cpu_label: str = HWS_HW_CPU):
+    def __init__(self, provider=None, dt: float = 0.1, cpu_label: str = CPU_LABEL):
         self.provider = provider if provider is not None else NVMLProvider()
         self.dt = dt
         self.cpu_label = cpu_label
@@ -133,10 +134,8 @@ class Sampler:
         for k in SERIES_GPU:
             self.data[k].append(r[k])
         cpu_use = float(self._psutil.cpu_percent()) if self._psutil else 0.0
-        spec = HWS_HARDWARE_SPECS[self.cpu_label]
         self.data["cpu_exe_utl"].append(cpu_use)
-        # linear power model of the reference (server.py:55-58)
-        self.data["cpu_psu"].append(max(cpu_use / 100 * spec["PSU_TDP"], spec["PSU_IDLE"]))
+        self.data["cpu_psu"].append(cpu_power_w(cpu_use, self.cpu_label))
         self.timestamps.append(time.time())
 
     def tick(self) -> int:

@@ -12,8 +12,8 @@ import socket
 
 import numpy as np
 
-from .constants import (HWS_DUMP_FORMAT, HWS_DUMP_JSON, HWS_DUMP_NPZ, SERV_ORDER_DUMP, SERV_ORDER_START,
-                        SERV_ORDER_STOP, SERV_ORDER_TICK, SOCKET_DIRECTORY, SOCKET_FILENAME)
+from . import protocol
+from .protocol import DumpFormat, Order
 from .sampler import NVMLProvider, Sampler
 
 
@@ -23,24 +23,23 @@ async def _sample_loop(sampler: Sampler, dt: float):
         await asyncio.sleep(dt)
 
 
-def dump(sampler: Sampler, name: str, fmt: str = HWS_DUMP_FORMAT) -> str:
+def dump(sampler: Sampler, name: str, fmt=None) -> str:
     d = sampler.dump_dict()
-    if fmt == HWS_DUMP_NPZ:
+    fmt = DumpFormat(fmt) if fmt is not None else DumpFormat.from_env()
+    if fmt is DumpFormat.NPZ:
         path = f"{name}.npz"
         np.savez_compressed(path, **{k: np.asarray(v) for k, v in d.items()})
-    elif fmt == HWS_DUMP_JSON:
+    elif fmt is DumpFormat.JSON:
         path = f"{name}.json"
         with open(path, "w") as f:
             json.dump(d, f, indent=4)
-    else:
-        raise RuntimeWarning(f"Can't dump in unknown format {fmt}")
     return path
 
 
-async def main(provider=None, socket_filename: str = SOCKET_FILENAME):
+async def main(provider=None, socket_filename: str = protocol.SOCKET_PATH):
     print("NVML server up & waiting for connection")
     server = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
-    os.makedirs(os.path.dirname(socket_filename) or SOCKET_DIRECTORY, exist_ok=True)
+    os.makedirs(os.path.dirname(socket_filename) or ".", exist_ok=True)
     if os.path.exists(socket_filename):
         os.remove(socket_filename)
     server.bind(socket_filename)
@@ -56,21 +55,20 @@ async def main(provider=None, socket_filename: str = SOCKET_FILENAME):
     task = None
     while True:
         client, _ = await loop.sock_accept(server)
-        request = (await loop.sock_recv(client, 255)).decode("utf8")
-        order = json.loads(request)
+        order = protocol.decode(await loop.sock_recv(client, 255))
         action = order.get("action")
-        if action == SERV_ORDER_STOP:
+        if action == Order.STOP.value:
             print("[NVML SERVER] Closing...")
             client.close()
             break
-        elif action == SERV_ORDER_START:
+        elif action == Order.START.value:
             sampler.dt = float(order["dt"])
             if task is None:
                 task = loop.create_task(_sample_loop(sampler, sampler.dt))
             print(f"[NVML SERVER] Recording every {sampler.dt} seconds")
-        elif action == SERV_ORDER_DUMP:
+        elif action == Order.DUMP.value:
             print(f"[NVML SERVER] Dumped {dump(sampler, order['dump_name'])}")
-        elif action == SERV_ORDER_TICK:
+        elif action == Order.TICK.value:
             print(f"[NVML SERVER] Recorded tick at {sampler.tick()}")
         else:
             print(f"[NVML SERVER] Received unknown {order}")
@@ -82,5 +80,5 @@ async def main(provider=None, socket_filename: str = SOCKET_FILENAME):
         os.remove(socket_filename)
 
 
-def cli(provider=None, socket_filename: str = SOCKET_FILENAME):
+def cli(provider=None, socket_filename: str = protocol.SOCKET_PATH):
     asyncio.run(main(provider, socket_filename))

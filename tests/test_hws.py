@@ -8,7 +8,7 @@ import numpy as np
 
 from b200stencil.hws import FakeNVML, Sampler
 from b200stencil.hws import analysis
-from b200stencil.hws.client import client_main
+from b200stencil.hws.client import send_order
 from b200stencil.hws.sampler import decode_reasons
 
 
@@ -27,13 +27,13 @@ def test_server_client_roundtrip(tmp_path):
         if os.path.exists(sock):
             break
         time.sleep(0.1)
-    client_main("start", socket_filename=sock)
+    send_order("start", socket_path=sock)
     time.sleep(0.5)
-    client_main("tick", socket_filename=sock)
+    send_order("tick", socket_path=sock)
     time.sleep(0.3)
-    client_main("dump", "hws_dump", socket_filename=sock)
+    send_order("dump", "hws_dump", socket_path=sock)
     time.sleep(0.3)
-    client_main("stop", socket_filename=sock)
+    send_order("stop", socket_path=sock)
     p.join(timeout=10)
     assert p.exitcode == 0
     path = tmp_path / "hws_dump.npz"
@@ -45,8 +45,23 @@ def test_server_client_roundtrip(tmp_path):
     assert d["cpu_exe_utl"].shape[0] == d["gpu_psu"].shape[0] == d["timestamps"].shape[0]
     assert 0 < int(d["ticks"][0]) <= d["gpu_psu"].shape[0]  # TICK = sample index, not len(dict)
     assert float(d["dt"]) == 0.1
-    rep = analysis.energy_envelop_calculation(d["cpu_psu"], d["gpu_psu"], d["timestamps"], verbose=False)
-    assert rep.GPU_envelop_kWh > 0 and rep.duration_s > 0
+    rep = analysis.energy_report(d["cpu_psu"], d["gpu_psu"], d["timestamps"])
+    assert rep.gpu_wh > 0 and rep.duration_s > 0 and "Wh" in rep.describe()
+
+
+def test_protocol_matches_the_reference_wire_format():
+    """START carries dt and dump_name, the others dump_name only (reference client.py:7-13, constants.py:33-46)."""
+    import json
+
+    from b200stencil.hws import protocol
+
+    assert json.loads(protocol.encode(protocol.Order.START)) == {"action": "START", "dt": 0.1, "dump_name": "hws_dump"}
+    assert json.loads(protocol.encode(protocol.Order.from_verb("dump"), "x")) == {"action": "DUMP", "dump_name": "x"}
+    assert protocol.SOCKET_PATH == "./sockets-runtime/hws"
+    import pytest
+
+    with pytest.raises(RuntimeError):
+        protocol.Order.from_verb("reboot")
 
 
 def test_sampler_thread_and_clock_summary():
@@ -62,6 +77,7 @@ def test_sampler_thread_and_clock_summary():
 
 def test_energy_exact_for_constant_power():
     t = np.arange(11) * 0.5  # 5 s
-    rep = analysis.energy_envelop_calculation(np.full(11, 360.0), np.full((11, 2), 720.0), t, verbose=False)
-    assert abs(rep.CPU_envelop_kWh - 0.36 * 5 / 3600) < 1e-12
-    assert abs(rep.GPU_envelop_kWh - 1.44 * 5 / 3600) < 1e-12
+    rep = analysis.energy_report(np.full(11, 360.0), np.full((11, 2), 720.0), t)
+    assert abs(rep.cpu_wh - 360.0 * 5 / 3600) < 1e-9
+    assert abs(rep.gpu_wh - 1440.0 * 5 / 3600) < 1e-9
+    assert abs(rep.total_kwh - (360.0 + 1440.0) * 5 / 3600 / 1000) < 1e-12
