@@ -153,6 +153,23 @@ def make(stencil: str, tiles: int, n: int, nk: int, dtype=torch.float64, seed: i
             sets.append((q, crx, xfx, cry, yfx, rarea, fields.empty(shp3, dtype, batch=tiles)))
         return Workload(name, stencil, pts, bpp, lambda s: stencils.fv_tp2d(*sets[s]), ns, keep=sets)
 
+    if stencil == "remap_delp":  # pe_prefix fused into the remap: delp, q1, pe2 in; q2 out
+        bpp = 4 * es
+        ns = slots or _slots_for(pts * bpp)
+        sets = []
+        for _ in range(ns):
+            delp = _rand(shp3, dtype, tiles, 0.5 * 1e5 / nk, 1.5 * 1e5 / nk, g)
+            pe1 = fields.empty((ni, nj, nk + 1), dtype, batch=tiles)
+            stencils.pe_prefix(delp, 1.0, pe1)
+            sig = (torch.arange(nk + 1, device="cuda", dtype=torch.float64) / nk).to(dtype)
+            pe2 = fields.empty((ni, nj, nk + 1), dtype, batch=tiles)
+            pe2[...] = pe1[..., :1] + (pe1[..., -1:] - pe1[..., :1]) * sig
+            pe2[..., -1] = pe1[..., -1]
+            del pe1
+            q1 = _rand(shp3, dtype, tiles, 1.0, 2.0, g)
+            sets.append((delp, 1.0, q1, pe2, fields.empty(shp3, dtype, batch=tiles)))
+        return Workload(name, stencil, pts, bpp, lambda s: stencils.remap_delp(*sets[s]), ns, keep=sets)
+
     if stencil in ("pe_prefix", "remap", "tridiag"):
         if stencil == "pe_prefix":
             bpp = 2 * es
@@ -191,12 +208,12 @@ def make(stencil: str, tiles: int, n: int, nk: int, dtype=torch.float64, seed: i
 
 ALL_STENCILS = [
     "top_of_column", "while_in_function", "hybrid_index_2dout", "find_klcl", "saturation_adjust", "cloud_top",
-    "fv_tp2d", "pe_prefix", "remap", "tridiag",
+    "fv_tp2d", "pe_prefix", "remap", "remap_delp", "tridiag",
 ]  # fmt: skip
 
 # stencil -> BASELINE config it is quoted on
 DEFAULT_CONFIG: Dict[str, str] = {
     "top_of_column": "C96x72", "while_in_function": "C96x72", "hybrid_index_2dout": "C96x72",
     "find_klcl": "C180x72", "saturation_adjust": "C180x72", "cloud_top": "C180x72",
-    "fv_tp2d": "C384x72", "pe_prefix": "C720x137", "remap": "C720x137", "tridiag": "C720x137",
+    "fv_tp2d": "C384x72", "pe_prefix": "C720x137", "remap": "C720x137", "remap_delp": "C720x137", "tridiag": "C720x137",
 }  # fmt: skip

@@ -32,6 +32,8 @@ SOURCES = {
     "k_fv.cu": [],
     "k_fv_direct.cu": [],
     "k_fv_tma.cu": [],
+    "tma_host.cu": [],
+    "k_remap_slab.cu": ["-fmad=false"],
     "k_halo.cu": [],
 }
 

@@ -17,57 +17,14 @@
 //   * every input element crosses HBM once; apron re-reads (q: (R+6)/R, cry/yfx: (R+1)/R) are
 //     L2 hits because neighbouring tiles are consecutive in the item order.
 // Algorithmic bytes/point: 40 R + 8 W + 8/nk (same as variant 1).
-#include <cuda.h>
-
-#include <map>
-#include <mutex>
-#include <tuple>
-
 #include "fv_math.cuh"
 #include "impl.cuh"
+#include "tma.cuh"
 
 namespace b2s {
 namespace impl {
 
 namespace {
-
-// ---- PTX wrappers (mbarrier + TMA) ------------------------------------------------------------
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
 
 constexpr int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
@@ -289,87 +246,7 @@ __global__ void __launch_bounds__(TI + 32) k_fv_tma(const __grid_constant__ CUte
   }
 }
 
-// ---- host side: tensor maps ---------------------------------------------------------------------
-
-using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeFn encode_fn() {
-  static EncodeFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeFn>(p);
-  });
-  return fn;
-}
-
-struct MapKey {
-  const void* base;
-  int64_t sj, sk, sb;
-  int e0, e1, e2, e3, b0, b1, es;
-  bool operator<(const MapKey& o) const {
-    return std::tie(base, sj, sk, sb, e0, e1, e2, e3, b0, b1, es) <
-           std::tie(o.base, o.sj, o.sk, o.sb, o.e0, o.e1, o.e2, o.e3, o.b0, o.b1, o.es);
-  }
-};
-std::map<MapKey, CUtensorMap> g_maps;
-std::mutex g_maps_mu;
-
-// A field as TMA sees it: 16-byte aligned base `p - off` (off elements), extents in elements.
-template <typename T>
-struct TmaField {
-  const T* base;
-  int off;
-  bool ok;
-};
-
-template <typename T>
-TmaField<T> tma_field(const T* first, int64_t sj, int64_t sk, int64_t sb, int nk, int nb) {
-  constexpr int V = 16 / sizeof(T);
-  TmaField<T> f;
-  const uintptr_t a = reinterpret_cast<uintptr_t>(first);
-  f.off = static_cast<int>((a % 16) / sizeof(T));
-  f.base = first - f.off;
-  f.ok = (a % sizeof(T) == 0) && sj > 0 && sj % V == 0 && (nk == 1 || (sk > 0 && sk % V == 0)) &&
-         (nb == 1 || (sb > 0 && sb % V == 0));
-  return f;
-}
-
-template <typename T>
-bool make_map(CUtensorMap* out, const T* base, int64_t sj, int64_t sk, int64_t sb, int e0, int e1, int e2, int e3,
-              int b0, int b1) {
-  MapKey key{base, sj, sk, sb, e0, e1, e2, e3, b0, b1, (int)sizeof(T)};
-  {
-    std::lock_guard<std::mutex> lk(g_maps_mu);
-    auto it = g_maps.find(key);
-    if (it != g_maps.end()) {
-      *out = it->second;
-      return true;
-    }
-  }
-  EncodeFn enc = encode_fn();
-  if (!enc) return false;
-  // size-1 axes still need a legal (multiple-of-16, non-zero) stride
-  const int64_t sk_b = (e2 > 1 ? sk : sj * e1) * (int64_t)sizeof(T);
-  const int64_t sb_b = (e3 > 1 ? sb : (e2 > 1 ? sk * e2 : sj * e1)) * (int64_t)sizeof(T);
-  cuuint64_t dims[4] = {(cuuint64_t)e0, (cuuint64_t)e1, (cuuint64_t)e2, (cuuint64_t)e3};
-  cuuint64_t strides[3] = {(cuuint64_t)(sj * sizeof(T)), (cuuint64_t)sk_b, (cuuint64_t)sb_b};
-  cuuint32_t box[4] = {(cuuint32_t)b0, (cuuint32_t)b1, 1, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  const CUtensorMapDataType dt = sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-  CUresult r = enc(out, dt, 4, const_cast<T*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return false;
-  std::lock_guard<std::mutex> lk(g_maps_mu);
-  if (g_maps.size() > 256) g_maps.clear();
-  g_maps[key] = *out;
-  return true;
-}
+// ---- host side (tensor maps: tma.cuh / tma_host.cu) ------------------------------------------------
 
 template <typename T, int TI, int R, int NSTAGE>
 int launch(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j1, F3<const T> q, F3<const T> crx,

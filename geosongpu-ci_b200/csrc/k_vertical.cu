@@ -119,12 +119,43 @@ __global__ void __launch_bounds__(kBlock, MINB) k_remap_nested(int ni, int nj, i
   }
 }
 
+// slab variant (k_remap_slab.cu): source column block staged in shared memory
+template <typename T, bool DELP>
+int remap_slab(int variant, int ni, int nj, int nk1, int nk2, int nb, T ptop, F3<const T> e1, F3<const T> q1,
+               F3<const T> pe2, F3<T> q2, cudaStream_t s, bool* applicable);
+
+// b2s_set_option("remap_variant", v): 0 auto (slab with TMA loads where the fields allow it, else slab
+// with cp.async loads, else nested), 1 nested (thread per column), 2 slab + cp.async, 3 slab + TMA.
+template <typename T, bool DELP>
+int remap_try_slab(const char* what, int ni, int nj, int nk1, int nk2, int nb, T ptop, F3<const T> e1, F3<const T> q1,
+                   F3<const T> pe2, F3<T> q2, cudaStream_t s, bool* done) {
+  *done = false;
+  const int variant = option("remap_variant", 0);
+  if (variant == 1) return B2S_OK;
+  int rc = B2S_OK;
+  if (variant == 0 || variant == 3) {
+    rc = remap_slab<T, DELP>(3, ni, nj, nk1, nk2, nb, ptop, e1, q1, pe2, q2, s, done);
+    if (*done) return rc;
+    if (variant == 3)
+      return set_error(B2S_EUNSUPPORTED, "%s: remap_variant=3 forced but the fields do not meet the TMA rules", what);
+  }
+  rc = remap_slab<T, DELP>(2, ni, nj, nk1, nk2, nb, ptop, e1, q1, pe2, q2, s, done);
+  if (!*done && variant == 2)
+    return set_error(B2S_EUNSUPPORTED, "%s: remap_variant=2 forced but %d source levels do not fit shared memory", what, nk1);
+  return rc;
+}
+
 template <typename T>
 int remap(int ni, int nj, int nk1, int nk2, int nb, F3<const T> pe1, F3<const T> q1, F3<const T> pe2, F3<T> q2,
           cudaStream_t s) {
   B2S_ARGCHECK(ni > 0 && nj > 0 && nk1 > 0 && nk2 > 0 && nb > 0, "remap: empty domain %dx%dx(%d->%d)x%d", ni, nj, nk1,
                nk2, nb);
   B2S_ARGCHECK(pe1.p && q1.p && pe2.p && q2.p, "remap: null field");
+  {
+    bool done = false;
+    const int rc = remap_try_slab<T, false>("remap", ni, nj, nk1, nk2, nb, T(0), pe1, q1, pe2, q2, s, &done);
+    if (done || rc != B2S_OK) return rc;
+  }
   const int ncols = ni * nj * nb;
   const int grid = (ncols + kBlock - 1) / kBlock;
   k_remap_nested<T, 12><<<grid, kBlock, 0, s>>>(ni, nj, nk1, nk2, ncols, pe1, q1, pe2, q2);
@@ -182,6 +213,11 @@ int remap_delp(int ni, int nj, int nk1, int nk2, int nb, T ptop, F3<const T> del
   B2S_ARGCHECK(ni > 0 && nj > 0 && nk1 > 0 && nk2 > 0 && nb > 0, "remap_delp: empty domain %dx%dx(%d->%d)x%d", ni, nj,
                nk1, nk2, nb);
   B2S_ARGCHECK(delp.p && q1.p && pe2.p && q2.p, "remap_delp: null field");
+  {
+    bool done = false;
+    const int rc = remap_try_slab<T, true>("remap_delp", ni, nj, nk1, nk2, nb, ptop, delp, q1, pe2, q2, s, &done);
+    if (done || rc != B2S_OK) return rc;
+  }
   const int ncols = ni * nj * nb;
   k_remap_delp<T><<<(ncols + kBlock - 1) / kBlock, kBlock, 0, s>>>(ni, nj, nk1, nk2, ncols, ptop, delp, q1, pe2, q2);
   return check_launch("remap_delp");

@@ -24,6 +24,7 @@ static std::map<std::string, int> g_options = {
     {"fv_ti", 0},           // TMA tile width: 0 auto, 32 | 64 | 96 | 128 | 192 (k_fv_tma.cu)
     {"fv_rows", 0},         // rows per stage: 0 auto, 4 | 8
     {"fv_stages", 0},       // mbarrier ring depth: 0 auto, 2 | 3
+    {"remap_variant", 0},   // 0 auto, 1 nested (thread per column), 2 slab + cp.async, 3 slab + TMA (k_remap_slab.cu)
     {"sat_unroll", 0},      // levels per load batch of k_saturation_adjust: 0 auto, 1 | 2 | 4
     {"sat_kchunk", 0},      // levels per thread of k_saturation_adjust: 0 auto (8)
 };

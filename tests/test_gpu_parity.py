@@ -317,6 +317,110 @@ def test_vertical(st, shape, dtype):
     assert_close(down(x), ref, RTOL[dtype], "x")
 
 
+REMAP_VARIANTS = {1: "nested (thread per column)", 2: "slab + cp.async", 3: "slab + TMA"}
+
+
+@pytest.fixture
+def remap_variant():
+    """Force one remap kernel for a test and restore the automatic choice afterwards."""
+    from b200stencil import _abi
+
+    yield lambda v: _abi.set_option("remap_variant", v)
+    _abi.set_option("remap_variant", 0)
+
+
+def _degenerate_vertical(ni, nj, nk, nk2, dtype):
+    """Edge cases of the marching pointer: zero-thickness source layers, target edges that coincide with
+    source edges, and a target column that starts above and ends below the source column."""
+    v = gen.vertical_inputs(ni, nj, nk, dtype, nk2=nk2)
+    delp = np.array(v["delp"])
+    delp[:, :, 2::5] = 0  # zero-thickness layers
+    pe1 = np.empty((ni, nj, nk + 1), dtype)
+    pe1[:, :, 0] = v["ptop"]
+    for k in range(nk):
+        pe1[:, :, k + 1] = pe1[:, :, k] + delp[:, :, k]
+    span = pe1[:, :, -1:] - pe1[:, :, :1]
+    sig = (np.arange(nk2 + 1, dtype=np.float64) / nk2).astype(dtype)
+    pe2 = (pe1[:, :, :1] - dtype(0.05) * span + dtype(1.1) * span * sig[None, None, :]).astype(dtype)
+    m = min(nk, nk2)
+    pe2[::2, :, 1:m:3] = pe1[::2, :, 1:m:3]  # coinciding edges (kept monotone below)
+    for k in range(1, nk2 + 1):  # strictly increasing target edges (a zero-thickness target layer divides 0/0)
+        prev = pe2[:, :, k - 1]
+        pe2[:, :, k] = np.where(pe2[:, :, k] > prev, pe2[:, :, k], np.nextafter(prev, dtype(np.inf)))
+    return {"delp": gen.as_ifirst(delp), "pe1": gen.as_ifirst(pe1), "pe2": gen.as_ifirst(pe2), "q1": v["q1"], "ptop": v["ptop"]}
+
+
+@pytest.mark.parametrize("variant", sorted(REMAP_VARIANTS))
+@pytest.mark.parametrize("shape", [(3, 3, 4, 4), (40, 9, 72, 75), (70, 5, 137, 150), (33, 4, 20, 90), (64, 6, 100, 30), (96, 2, 137, 137)])
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_remap_variants_bit_identical(st, remap_variant, variant, shape, dtype):
+    """Every remap kernel (thread-per-column, shared-memory slab with cp.async or TMA loads) must give the
+    oracle's bits: same overlaps, same order of accumulation (k_remap_slab.cu replaces the marching start
+    by a binary search, which is the same layer for monotone edges)."""
+    ni, nj, nk, nk2 = shape
+    for v in (gen.vertical_inputs(ni, nj, nk, dtype, nk2=nk2), _degenerate_vertical(ni, nj, nk, nk2, dtype)):
+        ref = zeros_like_np((ni, nj, nk2), dtype)
+        orc.remap(v["pe1"], v["q1"], v["pe2"], ref)
+        remap_variant(variant)
+        q2 = up(np.zeros((ni, nj, nk2), dtype))
+        st.remap(up(v["pe1"]), up(v["q1"]), up(v["pe2"]), q2)
+        assert np.array_equal(down(q2), ref), f"remap, {REMAP_VARIANTS[variant]}"
+        q2f = up(np.zeros((ni, nj, nk2), dtype))
+        st.remap_delp(up(v["delp"]), v["ptop"], up(v["q1"]), up(v["pe2"]), q2f)
+        assert np.array_equal(down(q2f), ref), f"remap_delp, {REMAP_VARIANTS[variant]}"
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_remap_slab_unaligned_and_batched(st, remap_variant, dtype):
+    """Fields that start off a 16-byte boundary (interior windows of halo-padded storage) cannot be TMA
+    sources: the automatic choice must fall back to the cp.async loader, forcing TMA must fail loudly,
+    and a batch of sub-domains in one launch must equal the per-sub-domain results."""
+    from b200stencil import _abi, fields
+
+    ni, nj, nk, nk2, nb, h = 45, 7, 72, 72, 3, 3
+    vs = [gen.vertical_inputs(ni, nj, nk, dtype, cfg=5 + b, nk2=nk2) for b in range(nb)]
+    refs = []
+    for v in vs:
+        r = zeros_like_np((ni, nj, nk2), dtype)
+        orc.remap(v["pe1"], v["q1"], v["pe2"], r)
+        refs.append(r)
+
+    def padded(name, levels):
+        big = fields.zeros((ni + 2 * h, nj + 2 * h, levels), dtype=tdt(dtype), batch=nb)
+        win = big[:, h:h + ni, h:h + nj, :]
+        for b, v in enumerate(vs):
+            win[b].copy_(torch.from_numpy(np.ascontiguousarray(v[name])))
+        return win
+
+    pe1, q1, pe2, delp = padded("pe1", nk + 1), padded("q1", nk), padded("pe2", nk2 + 1), padded("delp", nk)
+    assert pe1.data_ptr() % 16 != 0  # a 3-cell halo offsets the window by 24 (fp64) / 12 (fp32) bytes
+    for variant in (0, 1, 2):
+        remap_variant(variant)
+        q2 = fields.zeros((ni, nj, nk2), dtype=tdt(dtype), batch=nb)
+        st.remap(pe1, q1, pe2, q2)
+        q2f = fields.zeros((ni, nj, nk2), dtype=tdt(dtype), batch=nb)
+        st.remap_delp(delp, vs[0]["ptop"], q1, pe2, q2f)
+        for b in range(nb):
+            assert np.array_equal(down(q2[b]), refs[b]), (variant, b)
+            assert np.array_equal(down(q2f[b]), refs[b]), (variant, b)
+    remap_variant(3)
+    with pytest.raises(_abi.B200StencilError):
+        st.remap(pe1, q1, pe2, fields.zeros((ni, nj, nk2), dtype=tdt(dtype), batch=nb))
+
+
+def test_remap_tall_columns_fall_back(st, remap_variant):
+    """More source levels than two resident slabs allow: the automatic choice is the nested kernel."""
+    ni, nj, nk = 8, 3, 600
+    v = gen.vertical_inputs(ni, nj, nk, np.float64, nk2=nk)
+    ref = zeros_like_np((ni, nj, nk), np.float64)
+    orc.remap(v["pe1"], v["q1"], v["pe2"], ref)
+    remap_variant(0)
+    q2 = up(np.zeros((ni, nj, nk)))
+    st.remap(up(v["pe1"]), up(v["q1"]), up(v["pe2"]), q2)
+    assert np.array_equal(down(q2), ref)
+
+
+
 # ---- error channel ---------------------------------------------------------------------------------------
 
 
