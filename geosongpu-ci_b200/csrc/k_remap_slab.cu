@@ -32,10 +32,6 @@ namespace impl {
 
 namespace {
 
-constexpr int kCols = 32;   // columns per CTA (lane = column)
-constexpr int kWarps = 8;   // warps per CTA (one chunk of target levels each)
-constexpr int kThreads = kCols * kWarps;
-
 template <typename T>
 struct SlabParams {
   int ni, nj, nk1, nk2, ntile_i;
@@ -45,145 +41,198 @@ struct SlabParams {
   F3<T> q2;
 };
 
+// Geometry of a CTA: CG column groups of 32 columns (slab rows of 32*CG elements: 256 B for fp64 with
+// CG = 1 and for fp32 with CG = 2), NW warps per column group, each marching a chunk of CH target levels.
+template <int NW, int CG>
+struct SlabGeom {
+  static constexpr int COLS = 32 * CG;
+  static constexpr int THREADS = 32 * NW * CG;
+};
+
 // LOADER: 0 = cp.async per element, 1 = TMA tile loads
-template <typename T, int CH, bool DELP, int LOADER, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB) k_remap_slab(const __grid_constant__ CUtensorMap tm_e,
-                                                               const __grid_constant__ CUtensorMap tm_q,
-                                                               const SlabParams<T> P) {
+template <typename T, int CH, int NW, int CG, bool DELP, int LOADER, int MINB>
+__global__ void __launch_bounds__(32 * NW * CG, MINB) k_remap_slab(const __grid_constant__ CUtensorMap tm_e,
+                                                                   const __grid_constant__ CUtensorMap tm_q,
+                                                                   const SlabParams<T> P) {
+  constexpr int COLS = SlabGeom<NW, CG>::COLS;
   extern __shared__ __align__(1024) unsigned char smem[];
   const int nk1 = P.nk1, nk2 = P.nk2;
-  T* E = reinterpret_cast<T*>(smem);            // [nk1+1][32] source edges
-  T* Q = E + (size_t)(nk1 + 1) * kCols;         // [nk1][32] source values
-  uint64_t* bar = reinterpret_cast<uint64_t*>(Q + (size_t)nk1 * kCols);
+  T* E = reinterpret_cast<T*>(smem);          // [nk1+1][COLS] source edges
+  T* Q = E + (size_t)(nk1 + 1) * COLS;        // [nk1][COLS] source values
+  uint64_t* bar = reinterpret_cast<uint64_t*>(Q + (size_t)nk1 * COLS);  // [0]: E slab, [1]: Q slab
 
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
+  const int warp = (threadIdx.x >> 5) % NW;   // chunk index inside the column group
+  const int col = (threadIdx.x >> 5) / NW * 32 + (threadIdx.x & 31);  // column of the block owned by this thread
   int t = blockIdx.x;
   const int ti = t % P.ntile_i;
   t /= P.ntile_i;
   const int j = t % P.nj;
   const int b = t / P.nj;
-  const int i = ti * kCols + lane;
+  const int i = ti * COLS + col;
   const bool valid = i < P.ni;
-  constexpr int E0 = DELP ? 1 : 0;              // first slab row the load fills
-  const int ke = DELP ? nk1 : nk1 + 1;          // levels of the e1 field
+  constexpr int E0 = DELP ? 1 : 0;            // first slab row the load fills
+  const int ke = DELP ? nk1 : nk1 + 1;        // levels of the e1 field
 
   // ---- 1. start the slab loads ----
   if (LOADER == 1) {
     if (threadIdx.x == 0) {
-      mbar_init(bar, 1);
+      mbar_init(&bar[0], 1);
+      mbar_init(&bar[1], 1);
       fence_barrier_init();
-      mbar_arrive_expect_tx(bar, (uint32_t)((ke + nk1) * kCols * sizeof(T)));
-      tma_load_4d(E + E0 * kCols, &tm_e, bar, ti * kCols, j, 0, b);
-      tma_load_4d(Q, &tm_q, bar, ti * kCols, j, 0, b);
+      mbar_arrive_expect_tx(&bar[0], (uint32_t)(ke * COLS * sizeof(T)));
+      tma_load_4d(E + E0 * COLS, &tm_e, &bar[0], ti * COLS, j, 0, b);
+      mbar_arrive_expect_tx(&bar[1], (uint32_t)(nk1 * COLS * sizeof(T)));
+      tma_load_4d(Q, &tm_q, &bar[1], ti * COLS, j, 0, b);
     }
   } else {
     if (valid) {
       const T* ep = P.e1.at(i, j, 0, b);
       const T* qp = P.q1.at(i, j, 0, b);
-      for (int k = warp; k < ke; k += kWarps) cp_async<sizeof(T)>(E + (k + E0) * kCols + lane, ep + (int64_t)k * P.e1.sk);
-      for (int k = warp; k < nk1; k += kWarps) cp_async<sizeof(T)>(Q + k * kCols + lane, qp + (int64_t)k * P.q1.sk);
+      for (int k = warp; k < ke; k += NW) cp_async<sizeof(T)>(E + (k + E0) * COLS + col, ep + (int64_t)k * P.e1.sk);
+      for (int k = warp; k < nk1; k += NW) cp_async<sizeof(T)>(Q + k * COLS + col, qp + (int64_t)k * P.q1.sk);
     }
     cp_async_commit();
   }
 
   // ---- 2. target edges of this warp's first chunk, in flight while the slab arrives ----
-  const T* e2 = P.pe2.at(valid ? i : 0, j, 0, b);
-  T* o2 = P.q2.at(valid ? i : 0, j, 0, b);
+  // (running pointers: one 64-bit add per level instead of a 64-bit multiply-add per access)
   int k2b = warp * CH;
+  const int64_t sk2 = P.pe2.sk, sko = P.q2.sk;
+  const T* e2 = P.pe2.at(valid ? i : 0, j, k2b, b);
+  T* o2 = P.q2.at(valid ? i : 0, j, k2b, b);
+  int nlev = valid ? min(CH, nk2 - k2b) : 0;  // target levels of this chunk (<= 0: none)
   T tgt[CH + 1];
+  {
+    const T* p = e2;
 #pragma unroll
-  for (int u = 0; u <= CH; ++u) tgt[u] = (valid && k2b + u <= nk2) ? __ldg(e2 + (int64_t)(k2b + u) * P.pe2.sk) : T(0);
+    for (int u = 0; u <= CH; ++u) {
+      tgt[u] = u <= nlev ? __ldg(p) : T(0);
+      p += sk2;
+    }
+  }
 
   // ---- 3. slab complete ----
   if (LOADER == 1) {
-    __syncthreads();  // the barrier word is initialised
-    mbar_wait(bar, 0);
+    __syncthreads();  // the barrier words are initialised
+    mbar_wait(&bar[0], 0);
   } else {
     cp_async_wait_all();
     __syncthreads();
   }
   if (DELP) {
-    // pe1[0] = ptop; pe1[k+1] = pe1[k] + delp[k]: warp 0, lane = column, 8 levels loaded ahead
-    if (warp == 0) {
+    // pe1[0] = ptop; pe1[k+1] = pe1[k] + delp[k], in place, sequential in k (the oracle's order of
+    // additions): ONE warp per column group, lane = column, the next 8 levels loaded while the current 8
+    // are added; the q1 slab is still arriving meanwhile.  The warp that does it rotates with the block
+    // index, so the extra instructions spread over the four schedulers of the SM.
+    if (warp == (int)(blockIdx.x % NW)) {
+      T* Ec = E + col;
       T acc = P.ptop;
-      E[lane] = acc;
-      for (int kb = 0; kb < nk1; kb += 8) {
-        T d[8];
+      Ec[0] = acc;
+      Ec += COLS;  // Ec[k * COLS] = delp[k] -> pe1[k + 1]
+      T d[8], dn[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) d[u] = kb + u < nk1 ? E[(kb + u + 1) * kCols + lane] : T(0);
+      for (int u = 0; u < 8; ++u) d[u] = u < nk1 ? Ec[u * COLS] : T(0);
+      int kb = 0;
+      for (; kb + 16 <= nk1; kb += 8) {  // this batch and the next are complete: no predicates
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
+        for (int u = 0; u < 8; ++u) dn[u] = Ec[(8 + u) * COLS];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          acc = acc + d[u];
+          Ec[u * COLS] = acc;
+          d[u] = dn[u];
+        }
+        Ec += 8 * COLS;
+      }
+      for (; kb < nk1; kb += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) dn[u] = kb + 8 + u < nk1 ? Ec[(8 + u) * COLS] : T(0);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
           if (kb + u < nk1) {
             acc = acc + d[u];
-            E[(kb + u + 1) * kCols + lane] = acc;
+            Ec[u * COLS] = acc;
           }
+          d[u] = dn[u];
+        }
+        Ec += 8 * COLS;
       }
     }
     __syncthreads();
   }
-  if (!valid) return;
+  if (LOADER == 1) mbar_wait(&bar[1], 0);
 
   // ---- 4. chunks of target levels ----
-  const T* El = E + lane;
-  const T* Ql = Q + lane;
-  for (;;) {
-    if (k2b >= nk2) break;
+  // Per target layer the oracle first skips the source layers that end at or above the layer's upper
+  // edge (`while bot <= lo`) and then accumulates overlaps until a source layer reaches the lower edge.
+  // A skipped layer has no overlap (min(hi,bot) <= lo), so running it through the accumulation loop adds
+  // nothing and advances the pointer just the same: one loop does both, with identical results.
+  const T* El = E + col;
+  const T* Ql = Q + col;
+  const int klast = nk1 - 1;
+  while (nlev > 0) {
     T lo = tgt[0];
     // first source layer whose lower edge lies below lo (or the last layer): where the oracle's
     // marching pointer stands when it reaches target level k2b
     int k1;
     {
-      int a = 0, z = nk1 - 1;
+      int a = 0, z = klast;
       while (a < z) {
         const int m = (a + z) >> 1;
-        if (El[(m + 1) * kCols] > lo) z = m; else a = m + 1;
+        if (El[(m + 1) * COLS] > lo) z = m; else a = m + 1;
       }
       k1 = a;
     }
-    T top = El[k1 * kCols], bot = El[(k1 + 1) * kCols], qv = Ql[k1 * kCols];
+    const T* Ek = El + k1 * COLS;  // Ek[0] = top edge of the layer in hand
+    const T* Qk = Ql + k1 * COLS;
+    T top = Ek[0], bot = Ek[COLS], qv = Qk[0];
+    T* op = o2;
 #pragma unroll
     for (int u = 0; u < CH; ++u) {
-      if (k2b + u < nk2) {
+      if (u < nlev) {
         const T hi = tgt[u + 1];
-        while (k1 < nk1 - 1 && bot <= lo) {
-          ++k1;
-          top = bot;
-          bot = El[(k1 + 1) * kCols];
-          qv = Ql[k1 * kCols];
-        }
         T acc = T(0);
         for (;;) {
           const T a = lo > top ? lo : top;
           const T c = hi < bot ? hi : bot;
           if (c > a) acc = acc + (c - a) * qv;
-          if (bot >= hi || k1 == nk1 - 1) break;
+          if (bot >= hi || k1 == klast) break;
           ++k1;
+          Ek += COLS;
+          Qk += COLS;
           top = bot;
-          bot = El[(k1 + 1) * kCols];
-          qv = Ql[k1 * kCols];
+          bot = Ek[COLS];
+          qv = Qk[0];
         }
-        __stcs(o2 + (int64_t)(k2b + u) * P.q2.sk, acc / (hi - lo));
+        __stcs(op, acc / (hi - lo));
+        op += sko;
         lo = hi;
       }
     }
-    k2b += kWarps * CH;
-    if (k2b >= nk2) break;
+    k2b += NW * CH;
+    nlev = min(CH, nk2 - k2b);
+    if (nlev <= 0) break;
+    e2 += (int64_t)(NW * CH) * sk2;
+    o2 += (int64_t)(NW * CH) * sko;
+    {
+      const T* p = e2;
 #pragma unroll
-    for (int u = 0; u <= CH; ++u) tgt[u] = (k2b + u <= nk2) ? __ldg(e2 + (int64_t)(k2b + u) * P.pe2.sk) : T(0);
+      for (int u = 0; u <= CH; ++u) {
+        tgt[u] = u <= nlev ? __ldg(p) : T(0);
+        p += sk2;
+      }
+    }
   }
 }
 
-template <typename T>
-size_t slab_bytes(int nk1) {
-  return (size_t)(2 * nk1 + 1) * kCols * sizeof(T) + 16;
-}
+size_t slab_bytes(int nk1, int cols, size_t elem) { return (size_t)(2 * nk1 + 1) * cols * elem + 16; }
 
-template <typename T, int CH, bool DELP, int LOADER, int MINB>
-int launch_slab(const CUtensorMap& me, const CUtensorMap& mq, const SlabParams<T>& P, int64_t grid, cudaStream_t s,
+template <typename T, int CH, int NW, int CG, bool DELP, int LOADER, int MINB>
+int launch_slab(const CUtensorMap& me, const CUtensorMap& mq, const SlabParams<T>& P, int nj, int nb, cudaStream_t s,
                 const char* what) {
-  auto kern = k_remap_slab<T, CH, DELP, LOADER, MINB>;
-  const size_t smem = slab_bytes<T>(P.nk1);
+  using G = SlabGeom<NW, CG>;
+  auto kern = k_remap_slab<T, CH, NW, CG, DELP, LOADER, MINB>;
+  const size_t smem = slab_bytes(P.nk1, G::COLS, sizeof(T));
   static size_t configured = 0;  // largest dynamic shared size this instance was opted in for
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -191,7 +240,8 @@ int launch_slab(const CUtensorMap& me, const CUtensorMap& mq, const SlabParams<T
     if (e != cudaSuccess) return set_error((int)e, "%s(slab): cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
     configured = smem;
   }
-  kern<<<(unsigned)grid, kThreads, smem, s>>>(me, mq, P);
+  const int64_t grid = (int64_t)P.ntile_i * nj * nb;
+  kern<<<(unsigned)grid, G::THREADS, smem, s>>>(me, mq, P);
   return check_launch(what);
 }
 
@@ -199,16 +249,28 @@ int launch_slab(const CUtensorMap& me, const CUtensorMap& mq, const SlabParams<T
 
 // variant: 2 = cp.async loader, 3 = TMA loader.  *applicable = false (and B2S_OK) when this shape
 // or alignment is outside what the slab kernel covers; the caller then uses the nested kernel.
+// Geometry (b2s_set_option "remap_nw" = 8 | 16 warps per column group, "remap_cg" = 1 | 2 column
+// groups; 0 = automatic, from the sweeps in profiles/): the TMA loader comes in 8x1, 16x1 and 8x2,
+// the cp.async loader (the path for fields TMA cannot address) in 8x1.
 template <typename T, bool DELP>
 int remap_slab(int variant, int ni, int nj, int nk1, int nk2, int nb, T ptop, F3<const T> e1, F3<const T> q1,
                F3<const T> pe2, F3<T> q2, cudaStream_t s, bool* applicable) {
   *applicable = false;
   const char* what = DELP ? "remap_delp" : "remap";
+  int nw = option("remap_nw", 0), cg = option("remap_cg", 0);
+  if (variant != 3) nw = 8, cg = 1;
+  if (cg == 0) cg = sizeof(T) == 4 ? 2 : 1;
+  if (cg == 2 && ni <= 32) cg = 1;
+  if (nw == 0) nw = 8;
+  if (cg == 2) nw = 8;
+  const int cols = 32 * cg;
   // at least two CTAs per SM must fit, or the loads of one CTA cannot overlap the march of another
-  if (2 * (slab_bytes<T>(nk1) + 1024) > (size_t)227 * 1024) return B2S_OK;
-  const int ntile_i = (ni + kCols - 1) / kCols;
-  const int64_t grid = (int64_t)ntile_i * nj * nb;
-  if (grid > 0x7fffffffLL) return B2S_OK;
+  if (2 * (slab_bytes(nk1, cols, sizeof(T)) + 1024) > (size_t)227 * 1024) {
+    if (cg == 2 && 2 * (slab_bytes(nk1, 32, sizeof(T)) + 1024) <= (size_t)227 * 1024) cg = 1;
+    else return B2S_OK;
+  }
+  const int ntile_i = (ni + 32 * cg - 1) / (32 * cg);
+  if ((int64_t)ntile_i * nj * nb > 0x7fffffffLL) return B2S_OK;
   SlabParams<T> P;
   P.ni = ni, P.nj = nj, P.nk1 = nk1, P.nk2 = nk2, P.ntile_i = ntile_i;
   P.ptop = ptop;
@@ -220,8 +282,8 @@ int remap_slab(int variant, int ni, int nj, int nk1, int nk2, int nb, T ptop, F3
     const TmaField<T> fe = tma_field<T>(e1.p, e1.sj, e1.sk, e1.sb, ke, nb);
     const TmaField<T> fq = tma_field<T>(q1.p, q1.sj, q1.sk, q1.sb, nk1, nb);
     tma = fe.ok && fq.ok && fe.off == 0 && fq.off == 0 &&
-          make_map<T>(&me, e1.p, e1.sj, e1.sk, e1.sb, ni, nj, ke, nb, kCols, 1, ke) &&
-          make_map<T>(&mq, q1.p, q1.sj, q1.sk, q1.sb, ni, nj, nk1, nb, kCols, 1, nk1);
+          make_map<T>(&me, e1.p, e1.sj, e1.sk, e1.sb, ni, nj, ke, nb, 32 * cg, 1, ke) &&
+          make_map<T>(&mq, q1.p, q1.sj, q1.sk, q1.sb, ni, nj, nk1, nb, 32 * cg, 1, nk1);
   }
   if (!tma) {
     if (variant == 3) return B2S_OK;  // TMA was asked for explicitly and does not apply
@@ -229,14 +291,15 @@ int remap_slab(int variant, int ni, int nj, int nk1, int nk2, int nb, T ptop, F3
     memset(&mq, 0, sizeof(mq));
   }
   *applicable = true;
-  // chunk length: 8 warps x CH levels cover the column in one round for nk2 <= 80 (CH = 10) or <= 144 (CH = 18)
-  const bool small = nk2 <= kWarps * 10;
-  if (tma) {
-    return small ? launch_slab<T, 10, DELP, 1, 3>(me, mq, P, grid, s, what)
-                 : launch_slab<T, 18, DELP, 1, 2>(me, mq, P, grid, s, what);
-  }
-  return small ? launch_slab<T, 10, DELP, 0, 3>(me, mq, P, grid, s, what)
-               : launch_slab<T, 18, DELP, 0, 2>(me, mq, P, grid, s, what);
+  // chunk length: NW warps x CH levels cover the column in one round for nk2 <= 9 NW (CH = 9), else CH = 18
+  // (8 warps: nk2 <= 144 in one round; 16 warps always march 9 levels per round)
+  const bool small = nk2 <= nw * 9 || nw == 16;
+#define B2S_SLAB(CH, NW, CG, LOADER, MINB) launch_slab<T, CH, NW, CG, DELP, LOADER, MINB>(me, mq, P, nj, nb, s, what)
+  if (!tma) return small ? B2S_SLAB(9, 8, 1, 0, 4) : B2S_SLAB(18, 8, 1, 0, 3);
+  if (cg == 2) return small ? B2S_SLAB(9, 8, 2, 1, 2) : B2S_SLAB(18, 8, 2, 1, sizeof(T) == 4 ? 2 : 1);
+  if (nw == 16) return B2S_SLAB(9, 16, 1, 1, 2);
+  return small ? B2S_SLAB(9, 8, 1, 1, 4) : B2S_SLAB(18, 8, 1, 1, 3);
+#undef B2S_SLAB
 }
 
 #define INSTANTIATE(T)                                                                                            \

@@ -317,7 +317,11 @@ def test_vertical(st, shape, dtype):
     assert_close(down(x), ref, RTOL[dtype], "x")
 
 
-REMAP_VARIANTS = {1: "nested (thread per column)", 2: "slab + cp.async", 3: "slab + TMA"}
+# (remap_variant, remap_nw, remap_cg): kernel, warps per column group, 32-column groups per CTA
+REMAP_VARIANTS = {
+    (1, 0, 0): "nested (thread per column)", (2, 0, 0): "slab + cp.async", (3, 0, 0): "slab + TMA, automatic geometry",
+    (3, 8, 1): "slab + TMA 8x1", (3, 16, 1): "slab + TMA 16x1", (3, 8, 2): "slab + TMA 8x2",
+}  # fmt: skip
 
 
 @pytest.fixture
@@ -325,8 +329,13 @@ def remap_variant():
     """Force one remap kernel for a test and restore the automatic choice afterwards."""
     from b200stencil import _abi
 
-    yield lambda v: _abi.set_option("remap_variant", v)
-    _abi.set_option("remap_variant", 0)
+    def force(v):
+        v = (v, 0, 0) if isinstance(v, int) else v
+        for name, x in zip(("remap_variant", "remap_nw", "remap_cg"), v):
+            _abi.set_option(name, x)
+
+    yield force
+    force(0)
 
 
 def _degenerate_vertical(ni, nj, nk, nk2, dtype):
@@ -351,7 +360,7 @@ def _degenerate_vertical(ni, nj, nk, nk2, dtype):
 
 
 @pytest.mark.parametrize("variant", sorted(REMAP_VARIANTS))
-@pytest.mark.parametrize("shape", [(3, 3, 4, 4), (40, 9, 72, 75), (70, 5, 137, 150), (33, 4, 20, 90), (64, 6, 100, 30), (96, 2, 137, 137)])
+@pytest.mark.parametrize("shape", [(3, 3, 4, 4), (40, 9, 72, 75), (70, 5, 137, 150), (33, 4, 20, 90), (64, 6, 100, 30), (96, 2, 137, 137), (65, 3, 72, 72)])
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_remap_variants_bit_identical(st, remap_variant, variant, shape, dtype):
     """Every remap kernel (thread-per-column, shared-memory slab with cp.async or TMA loads) must give the
