@@ -101,9 +101,8 @@ int cloud_top(int ni, int nj, int nk, int nb, T ql_min, F3<const T> ql, F2<typen
 
 // -------------------------------------------------------------------------------------------
 // K4b saturation_adjust: PARALLEL pointwise, two fixed Newton steps, in place on T, q, ql.
-// Algorithmic bytes/point: 32 R + 24 W = 56.  In fp64 the two exp() and the divisions put
-// ~170 DP operations on every point, close to the DFMA budget per point at HBM speed, so the
-// reciprocals of (T - 29.65) and (p - (1-eps) es) are formed once per step and reused.
+// Algorithmic bytes/point: 32 R + 24 W = 56.  The reciprocals of (T - 29.65) and (p - (1-eps) es)
+// are formed once per step and reused.
 // -------------------------------------------------------------------------------------------
 template <typename T>
 __device__ __forceinline__ T exp_(T x);
@@ -135,6 +134,67 @@ __device__ __forceinline__ void sat_adjust_point(T& t, T& qv, T& l, const T pp) 
   }
 }
 
+// fp64: the library exp() and the three IEEE divisions per Newton step cost ~400 issued instructions
+// per point (ncu/SASS: 242 DP operations plus ~330 moves that materialise 64-bit literals, plus the
+// slow-path checks of every division), which paces the kernel at ~90 Gpts/s = 78 % of the HBM
+// roofline: it was ISSUE-bound, not HBM-bound.  This version keeps every constant in constant
+// memory (DFMA/DMUL read c[bank][offset] operands directly, no moves), forms reciprocals from
+// MUFU.RCP64H + two Newton steps (<= 1 ulp, no slow path: the operands are O(1)..O(1e5) physical
+// values) and evaluates exp() as 2^k * P13(r), |r| <= ln2/2 (Taylor remainder 4e-18).  Total error
+// vs. the oracle's exp/divide is a few ulp, far inside the 1e-12 the specification asks for.
+struct SatConst {
+  double eps, one_m_eps, lcp, c2965, c27315, c1767, c6112, cdes;
+  double l2e, ln2hi, ln2lo, magic;
+  double p[14];  // 1/n!, n = 0..13
+};
+__constant__ SatConst kSat = {
+    0.622, 1.0 - 0.622, 2.5e6 / 1004.0, 29.65, 273.15, 17.67, 611.2, 17.67 * 243.5,
+    1.4426950408889634074, 6.93147180369123816490e-01, 1.90821492927058770002e-10, 6755399441055744.0,
+    {1.0, 1.0, 1.0 / 2, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320, 1.0 / 362880, 1.0 / 3628800,
+     1.0 / 39916800, 1.0 / 479001600, 1.0 / 6227020800.0}};
+
+__device__ __forceinline__ double rcp_newton(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));  // MUFU.RCP64H: ~20 good bits
+  double e = __fma_rn(-x, r, 1.0);
+  r = __fma_rn(r, e, r);
+  e = __fma_rn(-x, r, 1.0);
+  r = __fma_rn(r, e, r);
+  return r;
+}
+
+// exp(x) for |x| < 700 (here x = 17.67 (T-273.15)/(T-29.65), |x| < 40 for any T above 100 K)
+__device__ __forceinline__ double exp_poly(double x) {
+  const double tk = __fma_rn(x, kSat.l2e, kSat.magic);  // low word of tk = round(x log2 e)
+  const double kf = tk - kSat.magic;
+  double r = __fma_rn(-kf, kSat.ln2hi, x);
+  r = __fma_rn(-kf, kSat.ln2lo, r);
+  double p = kSat.p[13];
+#pragma unroll
+  for (int n = 12; n >= 0; --n) p = __fma_rn(p, r, kSat.p[n]);
+  int k = __double2loint(tk);
+  k = max(-1000, min(1000, k));
+  return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));  // p * 2^k, p in [0.7, 1.42]
+}
+
+template <>
+__device__ __forceinline__ void sat_adjust_point<double>(double& t, double& qv, double& l, const double pp) {
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const double rtm = rcp_newton(t - kSat.c2965);
+    const double es = kSat.c6112 * exp_poly(kSat.c1767 * (t - kSat.c27315) * rtm);
+    const double rden = rcp_newton(__fma_rn(-kSat.one_m_eps, es, pp));
+    const double qs = kSat.eps * es * rden;
+    const double des = es * kSat.cdes * rtm * rtm;
+    const double dqs = kSat.eps * pp * des * rden * rden;
+    double dq = (qv - qs) * rcp_newton(__fma_rn(kSat.lcp, dqs, 1.0));
+    dq = fmax(dq, -l);
+    t = __fma_rn(kSat.lcp, dq, t);
+    qv -= dq;
+    l += dq;
+  }
+}
+
 template <typename T, int W, int U>
 __global__ void __launch_bounds__(kBlock) k_saturation_adjust(int niw, int nj, int nk, int ncols, int kchunk,
                                                               F3<const T> p, F3<T> Tt, F3<T> q, F3<T> ql) {
@@ -143,25 +203,34 @@ __global__ void __launch_bounds__(kBlock) k_saturation_adjust(int niw, int nj, i
   const Col cc = decompose_column(c, niw, nj);
   const int i = cc.i * W;
   const int k0 = blockIdx.y * kchunk, k1 = min(nk, k0 + kchunk);
+  // running pointers: the index arithmetic of four strided fields is paid once per thread, not per level
+  T* pt = Tt.at(i, cc.j, k0, cc.b);
+  T* pq = q.at(i, cc.j, k0, cc.b);
+  T* pl = ql.at(i, cc.j, k0, cc.b);
+  const T* pp = p.at(i, cc.j, k0, cc.b);
   for (int kb = k0; kb < k1; kb += U) {
     Vec<T, W> vt[U], vq[U], vl[U], vp[U];
 #pragma unroll
     for (int u = 0; u < U; ++u)
       if (kb + u < k1) {
-        vt[u] = VecIO<T, W>::ld(Tt.at(i, cc.j, kb + u, cc.b));
-        vq[u] = VecIO<T, W>::ld(q.at(i, cc.j, kb + u, cc.b));
-        vl[u] = VecIO<T, W>::ld(ql.at(i, cc.j, kb + u, cc.b));
-        vp[u] = VecIO<T, W>::ld(p.at(i, cc.j, kb + u, cc.b));
+        vt[u] = VecIO<T, W>::ld(pt + u * Tt.sk);
+        vq[u] = VecIO<T, W>::ld(pq + u * q.sk);
+        vl[u] = VecIO<T, W>::ld(pl + u * ql.sk);
+        vp[u] = VecIO<T, W>::ld(pp + u * p.sk);
       }
 #pragma unroll
     for (int u = 0; u < U; ++u)
       if (kb + u < k1) {
 #pragma unroll
         for (int w = 0; w < W; ++w) sat_adjust_point<T>(vt[u].v[w], vq[u].v[w], vl[u].v[w], vp[u].v[w]);
-        VecIO<T, W>::st(Tt.at(i, cc.j, kb + u, cc.b), vt[u]);
-        VecIO<T, W>::st(q.at(i, cc.j, kb + u, cc.b), vq[u]);
-        VecIO<T, W>::st(ql.at(i, cc.j, kb + u, cc.b), vl[u]);
+        VecIO<T, W>::st(pt + u * Tt.sk, vt[u]);
+        VecIO<T, W>::st(pq + u * q.sk, vq[u]);
+        VecIO<T, W>::st(pl + u * ql.sk, vl[u]);
       }
+    pt += U * Tt.sk;
+    pq += U * q.sk;
+    pl += U * ql.sk;
+    pp += U * p.sk;
   }
 }
 
@@ -175,10 +244,13 @@ int saturation_adjust(int ni, int nj, int nk, int nb, F3<const T> p, F3<T> Tt, F
   const int ncols = (ni / W) * nj * nb;
   // pointwise: k is free to be split across blockIdx.y
   int kchunk = option("sat_kchunk", 0);
-  if (kchunk <= 0) kchunk = 4;  // measured best on C180x72 (profiles/): 4 levels per thread, 1 level per load batch
+  // measured on C180x72 (profiles/r01_sat_sweep.json): 4 levels per thread; fp64 loads 2 levels per batch
+  // (111.6 vs 102.5 Gpts/s), 8 or 12 levels per thread are 3-5 % slower
+  if (kchunk <= 0) kchunk = 4;
   if (kchunk > nk) kchunk = nk;
   dim3 grid((ncols + kBlock - 1) / kBlock, (nk + kchunk - 1) / kchunk);
-  const int unroll = option("sat_unroll", 0);
+  int unroll = option("sat_unroll", 0);
+  if (unroll == 0) unroll = sizeof(T) == 8 ? 2 : 1;
   if (wide) {
     if (unroll == 2)
       k_saturation_adjust<T, WMAX, 2><<<grid, kBlock, 0, s>>>(ni / W, nj, nk, ncols, kchunk, p, Tt, q, ql);

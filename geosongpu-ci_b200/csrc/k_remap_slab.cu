@@ -35,6 +35,7 @@ namespace {
 template <typename T>
 struct SlabParams {
   int ni, nj, nk1, nk2, ntile_i;
+  int off_e, off_q;  // TMA loader: elements between the 16-byte aligned tensor base and compute column 0
   T ptop;
   F3<const T> e1;  // pe1 (nk1+1 levels) or delp (nk1 levels)
   F3<const T> q1, pe2;
@@ -49,17 +50,35 @@ struct SlabGeom {
   static constexpr int THREADS = 32 * NW * CG;
 };
 
-// LOADER: 0 = cp.async per element, 1 = TMA tile loads
+// Shared-memory layout: [pad][E slab: nk1+1 rows][Q slab: nk1 rows][2 mbarriers].  TMA destinations must
+// be 128-byte aligned: the pad puts the first row the E load fills (row 1 for remap_delp) on a 128-byte
+// boundary, the Q slab starts on the next one.  rowb = slab row pitch in bytes.
+struct SlabLayout {
+  int e_off, q_off, bar_off, total;
+  __host__ __device__ SlabLayout(int nk1, int rowb, bool delp) {
+    e_off = delp ? (128 - rowb % 128) % 128 : 0;
+    q_off = (e_off + (nk1 + 1) * rowb + 127) / 128 * 128;
+    bar_off = (q_off + nk1 * rowb + 15) / 16 * 16;
+    total = bar_off + 16;
+  }
+};
+
+// LOADER: 0 = cp.async per element, 1 = TMA tile loads, 2 = TMA tile loads of fields that start off a
+// 16-byte boundary (interior windows of halo-padded storage): a TMA box must start 16-byte aligned in
+// global memory, so the box starts at the aligned column at or before the block's first one, the slab
+// rows are 16 bytes wider and every thread skips `off` leading elements.
 template <typename T, int CH, int NW, int CG, bool DELP, int LOADER, int MINB>
 __global__ void __launch_bounds__(32 * NW * CG, MINB) k_remap_slab(const __grid_constant__ CUtensorMap tm_e,
                                                                    const __grid_constant__ CUtensorMap tm_q,
                                                                    const SlabParams<T> P) {
-  constexpr int COLS = SlabGeom<NW, CG>::COLS;
+  constexpr int BCOLS = SlabGeom<NW, CG>::COLS;                            // columns of the block
+  constexpr int COLS = BCOLS + (LOADER == 2 ? 16 / (int)sizeof(T) : 0);  // slab row pitch in elements
   extern __shared__ __align__(1024) unsigned char smem[];
   const int nk1 = P.nk1, nk2 = P.nk2;
-  T* E = reinterpret_cast<T*>(smem);          // [nk1+1][COLS] source edges
-  T* Q = E + (size_t)(nk1 + 1) * COLS;        // [nk1][COLS] source values
-  uint64_t* bar = reinterpret_cast<uint64_t*>(Q + (size_t)nk1 * COLS);  // [0]: E slab, [1]: Q slab
+  const SlabLayout L(nk1, COLS * (int)sizeof(T), DELP);
+  T* E = reinterpret_cast<T*>(smem + L.e_off);              // [nk1+1][COLS] source edges
+  T* Q = reinterpret_cast<T*>(smem + L.q_off);              // [nk1][COLS] source values
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar_off);  // [0]: E slab, [1]: Q slab
 
   const int warp = (threadIdx.x >> 5) % NW;   // chunk index inside the column group
   const int col = (threadIdx.x >> 5) / NW * 32 + (threadIdx.x & 31);  // column of the block owned by this thread
@@ -68,21 +87,21 @@ __global__ void __launch_bounds__(32 * NW * CG, MINB) k_remap_slab(const __grid_
   t /= P.ntile_i;
   const int j = t % P.nj;
   const int b = t / P.nj;
-  const int i = ti * COLS + col;
+  const int i = ti * BCOLS + col;
   const bool valid = i < P.ni;
   constexpr int E0 = DELP ? 1 : 0;            // first slab row the load fills
   const int ke = DELP ? nk1 : nk1 + 1;        // levels of the e1 field
 
   // ---- 1. start the slab loads ----
-  if (LOADER == 1) {
+  if (LOADER != 0) {
     if (threadIdx.x == 0) {
       mbar_init(&bar[0], 1);
       mbar_init(&bar[1], 1);
       fence_barrier_init();
       mbar_arrive_expect_tx(&bar[0], (uint32_t)(ke * COLS * sizeof(T)));
-      tma_load_4d(E + E0 * COLS, &tm_e, &bar[0], ti * COLS, j, 0, b);
+      tma_load_4d(E + E0 * COLS, &tm_e, &bar[0], ti * BCOLS, j, 0, b);
       mbar_arrive_expect_tx(&bar[1], (uint32_t)(nk1 * COLS * sizeof(T)));
-      tma_load_4d(Q, &tm_q, &bar[1], ti * COLS, j, 0, b);
+      tma_load_4d(Q, &tm_q, &bar[1], ti * BCOLS, j, 0, b);
     }
   } else {
     if (valid) {
@@ -112,7 +131,7 @@ __global__ void __launch_bounds__(32 * NW * CG, MINB) k_remap_slab(const __grid_
   }
 
   // ---- 3. slab complete ----
-  if (LOADER == 1) {
+  if (LOADER != 0) {
     __syncthreads();  // the barrier words are initialised
     mbar_wait(&bar[0], 0);
   } else {
@@ -125,7 +144,7 @@ __global__ void __launch_bounds__(32 * NW * CG, MINB) k_remap_slab(const __grid_
     // are added; the q1 slab is still arriving meanwhile.  The warp that does it rotates with the block
     // index, so the extra instructions spread over the four schedulers of the SM.
     if (warp == (int)(blockIdx.x % NW)) {
-      T* Ec = E + col;
+      T* Ec = E + col + (LOADER == 2 ? P.off_e : 0);
       T acc = P.ptop;
       Ec[0] = acc;
       Ec += COLS;  // Ec[k * COLS] = delp[k] -> pe1[k + 1]
@@ -160,15 +179,15 @@ __global__ void __launch_bounds__(32 * NW * CG, MINB) k_remap_slab(const __grid_
     }
     __syncthreads();
   }
-  if (LOADER == 1) mbar_wait(&bar[1], 0);
+  if (LOADER != 0) mbar_wait(&bar[1], 0);
 
   // ---- 4. chunks of target levels ----
   // Per target layer the oracle first skips the source layers that end at or above the layer's upper
   // edge (`while bot <= lo`) and then accumulates overlaps until a source layer reaches the lower edge.
   // A skipped layer has no overlap (min(hi,bot) <= lo), so running it through the accumulation loop adds
   // nothing and advances the pointer just the same: one loop does both, with identical results.
-  const T* El = E + col;
-  const T* Ql = Q + col;
+  const T* El = E + col + (LOADER == 2 ? P.off_e : 0);
+  const T* Ql = Q + col + (LOADER == 2 ? P.off_q : 0);
   const int klast = nk1 - 1;
   while (nlev > 0) {
     T lo = tgt[0];
@@ -225,14 +244,17 @@ __global__ void __launch_bounds__(32 * NW * CG, MINB) k_remap_slab(const __grid_
   }
 }
 
-size_t slab_bytes(int nk1, int cols, size_t elem) { return (size_t)(2 * nk1 + 1) * cols * elem + 16; }
+// cols = slab row pitch in elements (block columns, + 16 bytes for the shifted TMA loader)
+size_t slab_bytes(int nk1, int cols, size_t elem, bool delp = true) {
+  return (size_t)SlabLayout(nk1, cols * (int)elem, delp).total;
+}
 
 template <typename T, int CH, int NW, int CG, bool DELP, int LOADER, int MINB>
 int launch_slab(const CUtensorMap& me, const CUtensorMap& mq, const SlabParams<T>& P, int nj, int nb, cudaStream_t s,
                 const char* what) {
   using G = SlabGeom<NW, CG>;
   auto kern = k_remap_slab<T, CH, NW, CG, DELP, LOADER, MINB>;
-  const size_t smem = slab_bytes(P.nk1, G::COLS, sizeof(T));
+  const size_t smem = slab_bytes(P.nk1, G::COLS + (LOADER == 2 ? 16 / (int)sizeof(T) : 0), sizeof(T), DELP);
   static size_t configured = 0;  // largest dynamic shared size this instance was opted in for
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -263,10 +285,10 @@ int remap_slab(int variant, int ni, int nj, int nk1, int nk2, int nb, T ptop, F3
   if (cg == 2 && ni <= 32) cg = 1;
   if (nw == 0) nw = 8;
   if (cg == 2) nw = 8;
-  const int cols = 32 * cg;
+  constexpr int V = 16 / (int)sizeof(T);
   // at least two CTAs per SM must fit, or the loads of one CTA cannot overlap the march of another
-  if (2 * (slab_bytes(nk1, cols, sizeof(T)) + 1024) > (size_t)227 * 1024) {
-    if (cg == 2 && 2 * (slab_bytes(nk1, 32, sizeof(T)) + 1024) <= (size_t)227 * 1024) cg = 1;
+  if (2 * (slab_bytes(nk1, 32 * cg + V, sizeof(T)) + 1024) > (size_t)227 * 1024) {
+    if (cg == 2 && 2 * (slab_bytes(nk1, 32 + V, sizeof(T)) + 1024) <= (size_t)227 * 1024) cg = 1;
     else return B2S_OK;
   }
   const int ntile_i = (ni + 32 * cg - 1) / (32 * cg);
@@ -274,16 +296,23 @@ int remap_slab(int variant, int ni, int nj, int nk1, int nk2, int nb, T ptop, F3
   SlabParams<T> P;
   P.ni = ni, P.nj = nj, P.nk1 = nk1, P.nk2 = nk2, P.ntile_i = ntile_i;
   P.ptop = ptop;
+  P.off_e = P.off_q = 0;
   P.e1 = e1, P.q1 = q1, P.pe2 = pe2, P.q2 = q2;
   const int ke = DELP ? nk1 : nk1 + 1;
   CUtensorMap me, mq;
   bool tma = variant == 3 && ke <= 256;
+  bool shifted = false;
   if (tma) {
     const TmaField<T> fe = tma_field<T>(e1.p, e1.sj, e1.sk, e1.sb, ke, nb);
     const TmaField<T> fq = tma_field<T>(q1.p, q1.sj, q1.sk, q1.sb, nk1, nb);
-    tma = fe.ok && fq.ok && fe.off == 0 && fq.off == 0 &&
-          make_map<T>(&me, e1.p, e1.sj, e1.sk, e1.sb, ni, nj, ke, nb, 32 * cg, 1, ke) &&
-          make_map<T>(&mq, q1.p, q1.sj, q1.sk, q1.sb, ni, nj, nk1, nb, 32 * cg, 1, nk1);
+    shifted = fe.off != 0 || fq.off != 0;
+    if (shifted) cg = 1, nw = 8;  // the shifted loader comes in one geometry
+    const int box = 32 * cg + (shifted ? V : 0);
+    P.off_e = fe.off, P.off_q = fq.off;
+    P.ntile_i = (ni + 32 * cg - 1) / (32 * cg);
+    tma = fe.ok && fq.ok &&
+          make_map<T>(&me, fe.base, e1.sj, e1.sk, e1.sb, ni + fe.off, nj, ke, nb, box, 1, ke) &&
+          make_map<T>(&mq, fq.base, q1.sj, q1.sk, q1.sb, ni + fq.off, nj, nk1, nb, box, 1, nk1);
   }
   if (!tma) {
     if (variant == 3) return B2S_OK;  // TMA was asked for explicitly and does not apply
@@ -296,6 +325,7 @@ int remap_slab(int variant, int ni, int nj, int nk1, int nk2, int nb, T ptop, F3
   const bool small = nk2 <= nw * 9 || nw == 16;
 #define B2S_SLAB(CH, NW, CG, LOADER, MINB) launch_slab<T, CH, NW, CG, DELP, LOADER, MINB>(me, mq, P, nj, nb, s, what)
   if (!tma) return small ? B2S_SLAB(9, 8, 1, 0, 4) : B2S_SLAB(18, 8, 1, 0, 3);
+  if (shifted) return small ? B2S_SLAB(9, 8, 1, 2, 3) : B2S_SLAB(18, 8, 1, 2, 3);
   if (cg == 2) return small ? B2S_SLAB(9, 8, 2, 1, 2) : B2S_SLAB(18, 8, 2, 1, sizeof(T) == 4 ? 2 : 1);
   if (nw == 16) return B2S_SLAB(9, 16, 1, 1, 2);
   return small ? B2S_SLAB(9, 8, 1, 1, 4) : B2S_SLAB(18, 8, 1, 1, 3);

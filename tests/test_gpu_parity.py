@@ -381,10 +381,11 @@ def test_remap_variants_bit_identical(st, remap_variant, variant, shape, dtype):
 
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_remap_slab_unaligned_and_batched(st, remap_variant, dtype):
-    """Fields that start off a 16-byte boundary (interior windows of halo-padded storage) cannot be TMA
-    sources: the automatic choice must fall back to the cp.async loader, forcing TMA must fail loudly,
-    and a batch of sub-domains in one launch must equal the per-sub-domain results."""
-    from b200stencil import _abi, fields
+    """Fields that start off a 16-byte boundary (interior windows of halo-padded storage, the usual case
+    for NDSL-style Quantities): the TMA loader starts its boxes at the aligned column before the window
+    (`LOADER == 2` in k_remap_slab.cu); every kernel must give the same bits, and a batch of sub-domains
+    in one launch must equal the per-sub-domain results."""
+    from b200stencil import fields
 
     ni, nj, nk, nk2, nb, h = 45, 7, 72, 72, 3, 3
     vs = [gen.vertical_inputs(ni, nj, nk, dtype, cfg=5 + b, nk2=nk2) for b in range(nb)]
@@ -394,16 +395,17 @@ def test_remap_slab_unaligned_and_batched(st, remap_variant, dtype):
         orc.remap(v["pe1"], v["q1"], v["pe2"], r)
         refs.append(r)
 
-    def padded(name, levels):
-        big = fields.zeros((ni + 2 * h, nj + 2 * h, levels), dtype=tdt(dtype), batch=nb)
-        win = big[:, h:h + ni, h:h + nj, :]
+    def padded(name, levels, hh=h):
+        big = fields.zeros((ni + 2 * hh, nj + 2 * hh, levels), dtype=tdt(dtype), batch=nb)
+        win = big[:, hh:hh + ni, hh:hh + nj, :]
         for b, v in enumerate(vs):
             win[b].copy_(torch.from_numpy(np.ascontiguousarray(v[name])))
         return win
 
-    pe1, q1, pe2, delp = padded("pe1", nk + 1), padded("q1", nk), padded("pe2", nk2 + 1), padded("delp", nk)
-    assert pe1.data_ptr() % 16 != 0  # a 3-cell halo offsets the window by 24 (fp64) / 12 (fp32) bytes
-    for variant in (0, 1, 2):
+    # q1 with a different halo than pe1/delp: the two slabs are shifted by different amounts
+    pe1, q1, pe2, delp = padded("pe1", nk + 1), padded("q1", nk, 1), padded("pe2", nk2 + 1), padded("delp", nk)
+    assert pe1.data_ptr() % 16 != 0 and q1.data_ptr() % 16 != 0  # 3 cells = 24 / 12 bytes, 1 cell = 8 / 4 bytes
+    for variant in (0, 1, 2, 3):
         remap_variant(variant)
         q2 = fields.zeros((ni, nj, nk2), dtype=tdt(dtype), batch=nb)
         st.remap(pe1, q1, pe2, q2)
@@ -412,9 +414,26 @@ def test_remap_slab_unaligned_and_batched(st, remap_variant, dtype):
         for b in range(nb):
             assert np.array_equal(down(q2[b]), refs[b]), (variant, b)
             assert np.array_equal(down(q2f[b]), refs[b]), (variant, b)
+
+
+def test_remap_tma_rules(st, remap_variant):
+    """Row strides that are not multiples of 16 bytes cannot be described by a tensor map: the automatic
+    choice uses the cp.async loader, forcing the TMA loader fails loudly (no silent change of kernel)."""
+    from b200stencil import _abi
+
+    ni, nj, nk = 33, 5, 20
+    v = gen.vertical_inputs(ni, nj, nk, np.float64, nk2=nk)
+    ref = zeros_like_np((ni, nj, nk), np.float64)
+    orc.remap(v["pe1"], v["q1"], v["pe2"], ref)
+    pe1, q1, pe2 = up(v["pe1"], align_rows=False), up(v["q1"], align_rows=False), up(v["pe2"], align_rows=False)
+    assert pe1.stride(1) % 2 == 1
+    remap_variant(0)
+    q2 = up(np.zeros((ni, nj, nk)))
+    st.remap(pe1, q1, pe2, q2)
+    assert np.array_equal(down(q2), ref)
     remap_variant(3)
     with pytest.raises(_abi.B200StencilError):
-        st.remap(pe1, q1, pe2, fields.zeros((ni, nj, nk2), dtype=tdt(dtype), batch=nb))
+        st.remap(pe1, q1, pe2, q2)
 
 
 def test_remap_tall_columns_fall_back(st, remap_variant):
