@@ -104,15 +104,97 @@ __global__ void __launch_bounds__(kBlock) k_while_in_function(int niw, int nj, i
   if (undefined && undefined_count) atomicAdd(undefined_count, (unsigned long long)undefined);
 }
 
+// Thin grids (C96x72: 55 296 columns, a third of the machine's thread slots) make the scan above
+// latency-bound: a column is one thread and its levels arrive in nk/U dependent batches.  Here the
+// column is cut into S segments of L levels, one thread each (CTA = 32*W columns x S segments): every
+// thread issues ALL its loads at once, finds the first hit of its segment, the segments exchange
+// that through shared memory (the k-carry of the BACKWARD scan is "the first hit below me"), and
+// each thread then writes its own levels.  Same values as the scan, one DRAM round trip deep.
+template <typename T, int W, int L>
+__global__ void __launch_bounds__(1024) k_while_ksplit(int niw, int nj, int nk, int ncols, T thr, F3<const T> in,
+                                                       F3<T> out, unsigned long long* undefined_count) {
+  extern __shared__ int first_hit[];  // [segment][32*W]
+  const int lane = threadIdx.x, seg = threadIdx.y, nseg = blockDim.y;
+  const int c = blockIdx.x * 32 + lane;
+  const bool valid = c < ncols;
+  const Col cc = decompose_column(valid ? c : 0, niw, nj);
+  const int i = cc.i * W;
+  const int k0 = seg * L;
+  const T* ip = in.at(i, cc.j, k0, cc.b);
+  T* op = out.at(i, cc.j, k0, cc.b);
+  Vec<T, W> x[L];
+#pragma unroll
+  for (int u = 0; u < L; ++u)
+    if (valid && k0 + u < nk) x[u] = VecIO<T, W>::ld(ip + (int64_t)u * in.sk);
+  int nxt[W];
+#pragma unroll
+  for (int w = 0; w < W; ++w) nxt[w] = nk;
+#pragma unroll
+  for (int u = L - 1; u >= 0; --u)
+    if (valid && k0 + u < nk) {
+#pragma unroll
+      for (int w = 0; w < W; ++w)
+        if (!(x[u].v[w] < thr)) nxt[w] = k0 + u;
+    }
+#pragma unroll
+  for (int w = 0; w < W; ++w) first_hit[(seg * 32 + lane) * W + w] = nxt[w];
+  __syncthreads();
+  if (!valid) return;
+  // the carry entering this segment from below: the first hit of the nearest lower segment that has one
+#pragma unroll
+  for (int w = 0; w < W; ++w) nxt[w] = nk;
+  for (int s2 = nseg - 1; s2 > seg; --s2) {
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      const int f = first_hit[(s2 * 32 + lane) * W + w];
+      if (f < nk) nxt[w] = f;
+    }
+  }
+  unsigned int undefined = 0;
+#pragma unroll
+  for (int u = L - 1; u >= 0; --u) {
+    const int k = k0 + u;
+    if (k < nk) {
+      Vec<T, W> r;
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        if (!(x[u].v[w] < thr)) nxt[w] = k;
+        undefined += (nxt[w] == nk);
+        r.v[w] = static_cast<T>(nxt[w] - k);
+      }
+      VecIO<T, W>::st(op + (int64_t)u * out.sk, r);
+    }
+  }
+  if (undefined && undefined_count) atomicAdd(undefined_count, (unsigned long long)undefined);
+}
+
+// b2s_set_option("while_variant", v): 0 auto (k-split on thin grids), 1 column scan, 2 k-split
+template <typename T, int W>
+int while_ksplit_launch(int niw, int nj, int nk, int ncols, T thr, F3<const T> in, F3<T> out, unsigned long long* cnt,
+                        cudaStream_t s) {
+  constexpr int L = 9;
+  const int nseg = (nk + L - 1) / L;
+  dim3 block(32, nseg);
+  const size_t smem = (size_t)nseg * 32 * W * sizeof(int);
+  k_while_ksplit<T, W, L><<<(ncols + 31) / 32, block, smem, s>>>(niw, nj, nk, ncols, thr, in, out, cnt);
+  return check_launch("while_in_function");
+}
+
 template <typename T>
 int while_in_function(int ni, int nj, int nk, int nb, T threshold, F3<const T> in_field, F3<T> out_field,
                       int64_t* undefined_count, cudaStream_t s) {
   B2S_ARGCHECK(ni > 0 && nj > 0 && nk > 0 && nb > 0, "while_in_function: empty domain %dx%dx%dx%d", ni, nj, nk, nb);
   B2S_ARGCHECK(in_field.p && out_field.p, "while_in_function: null field");
   constexpr int WMAX = MaxWidth<T>::value;
-  const bool wide = ni % WMAX == 0 && WidthProbe(WMAX, sizeof(T)).field(in_field).field(out_field).ok &&
-                    (int64_t)(ni / WMAX) * nj * nb >= (int64_t)sm_count() * 1024;
+  const bool aligned = ni % WMAX == 0 && WidthProbe(WMAX, sizeof(T)).field(in_field).field(out_field).ok;
+  const bool wide = aligned && (int64_t)(ni / WMAX) * nj * nb >= (int64_t)sm_count() * 1024;
   auto* cnt = reinterpret_cast<unsigned long long*>(undefined_count);
+  const int variant = option("while_variant", 0);
+  const bool thin = (int64_t)ni * nj * nb < (int64_t)sm_count() * 2048;  // fewer columns than thread slots
+  if (variant != 1 && nk <= 9 * 32 && (variant == 2 || thin)) {
+    if (aligned) return while_ksplit_launch<T, WMAX>(ni / WMAX, nj, nk, (ni / WMAX) * nj * nb, threshold, in_field, out_field, cnt, s);
+    return while_ksplit_launch<T, 1>(ni, nj, nk, ni * nj * nb, threshold, in_field, out_field, cnt, s);
+  }
   if (wide) {
     const int ncols = (ni / WMAX) * nj * nb;
     k_while_in_function<T, WMAX, 8>

@@ -24,6 +24,7 @@ static std::map<std::string, int> g_options = {
     {"fv_ti", 0},           // TMA tile width: 0 auto, 32 | 64 | 96 | 128 | 192 (k_fv_tma.cu)
     {"fv_rows", 0},         // rows per stage: 0 auto, 4 | 8
     {"fv_stages", 0},       // mbarrier ring depth: 0 auto, 2 | 3
+    {"while_variant", 0},   // while_in_function: 0 auto, 1 column scan, 2 k-split (k_patterns.cu)
     {"remap_variant", 0},   // 0 auto, 1 nested (thread per column), 2 slab + cp.async, 3 slab + TMA (k_remap_slab.cu)
     {"remap_nw", 0},        // slab kernel: warps per column group, 0 auto, 8 | 16
     {"remap_cg", 0},        // slab kernel: 32-column groups per CTA, 0 auto (1 for fp64, 2 for fp32), 1 | 2

@@ -115,6 +115,37 @@ def test_while_undefined_is_counted(st):
     st.while_in_function(up(I), O)  # NULL counter is allowed
 
 
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("shape", [(3, 3, 4), (33, 5, 72), (64, 4, 137), (17, 3, 9), (8, 2, 10), (6, 2, 300)])
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_while_variants(st, variant, shape, dtype):
+    """Column scan and k-split kernels of while_in_function (k_patterns.cu) against the oracle, with sparse
+    hits (whole segments without one, so the carry crosses several segments) and undefined points."""
+    from b200stencil import _abi
+
+    ni, nj, nk = shape
+    rng = np.random.default_rng(7)
+    I = rng.uniform(0.0, 3.999, shape).astype(dtype)
+    hits = rng.integers(0, nk, size=(ni, nj, 2))
+    for a in range(ni):
+        for b in range(nj):
+            if (a + b) % 5:  # every fifth column has no hit at all: undefined everywhere
+                I[a, b, hits[a, b]] = 4.0 + rng.random(2) * 30
+    I = gen.as_ifirst(I)
+    ref = zeros_like_np(shape, dtype)
+    n = orc.while_in_function_scan(I, ref)
+    assert n > 0
+    _abi.set_option("while_variant", variant)
+    try:
+        for align in (True, False):
+            O = up(np.zeros(shape, dtype), align)
+            cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+            st.while_in_function(up(I, align), O, undefined_count=cnt)
+            assert np.array_equal(down(O), ref) and int(cnt.item()) == n
+    finally:
+        _abi.set_option("while_variant", 0)
+
+
 def test_hybrid_arbitrary_mask_last_match_wins(st):
     data, kmask, kidx = gen.hybrid_inputs(8, 6, 10)
     rng = np.random.default_rng(5)
