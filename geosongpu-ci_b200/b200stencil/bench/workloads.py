@@ -170,6 +170,27 @@ def make(stencil: str, tiles: int, n: int, nk: int, dtype=torch.float64, seed: i
             sets.append((delp, 1.0, q1, pe2, fields.empty(shp3, dtype, batch=tiles)))
         return Workload(name, stencil, pts, bpp, lambda s: stencils.remap_delp(*sets[s]), ns, keep=sets)
 
+    if stencil == "remap_ppm":  # FV3-style PPM remap: pe1, q1, pe2 in; q2 out
+        bpp = 4 * es
+        ns = slots or _slots_for(pts * bpp)
+        sets = []
+        for _ in range(ns):
+            delp = _rand(shp3, dtype, tiles, 0.5 * 1e5 / nk, 1.5 * 1e5 / nk, g)
+            pe1 = fields.empty((ni, nj, nk + 1), dtype, batch=tiles)
+            stencils.pe_prefix(delp, 1.0, pe1)
+            del delp
+            sig = (torch.arange(nk + 1, device="cuda", dtype=torch.float64) / nk).to(dtype)
+            pe2 = fields.empty((ni, nj, nk + 1), dtype, batch=tiles)
+            pe2[...] = pe1[..., :1] + (pe1[..., -1:] - pe1[..., :1]) * sig
+            pe2[..., -1] = pe1[..., -1]
+            pm = (0.5 * (pe1[..., 1:] + pe1[..., :-1]) / pe1[..., -1:]).to(torch.float64)
+            q1 = fields.empty(shp3, dtype, batch=tiles)
+            q1[...] = (1.0 + 0.6 * torch.sin(2 * math.pi * pm) + 0.3 * torch.sin(7 * math.pi * pm * pm)).to(dtype)
+            q1 += _rand(shp3, dtype, tiles, -0.02, 0.02, g)
+            del pm
+            sets.append((pe1, q1, pe2, fields.empty(shp3, dtype, batch=tiles)))
+        return Workload(name, stencil, pts, bpp, lambda s: stencils.remap_ppm(*sets[s]), ns, keep=sets)
+
     if stencil in ("pe_prefix", "remap", "tridiag"):
         if stencil == "pe_prefix":
             bpp = 2 * es
@@ -208,12 +229,12 @@ def make(stencil: str, tiles: int, n: int, nk: int, dtype=torch.float64, seed: i
 
 ALL_STENCILS = [
     "top_of_column", "while_in_function", "hybrid_index_2dout", "find_klcl", "saturation_adjust", "cloud_top",
-    "fv_tp2d", "pe_prefix", "remap", "remap_delp", "tridiag",
+    "fv_tp2d", "pe_prefix", "remap", "remap_delp", "remap_ppm", "tridiag",
 ]  # fmt: skip
 
 # stencil -> BASELINE config it is quoted on
 DEFAULT_CONFIG: Dict[str, str] = {
     "top_of_column": "C96x72", "while_in_function": "C96x72", "hybrid_index_2dout": "C96x72",
     "find_klcl": "C180x72", "saturation_adjust": "C180x72", "cloud_top": "C180x72",
-    "fv_tp2d": "C384x72", "pe_prefix": "C720x137", "remap": "C720x137", "remap_delp": "C720x137", "tridiag": "C720x137",
+    "fv_tp2d": "C384x72", "pe_prefix": "C720x137", "remap": "C720x137", "remap_delp": "C720x137", "remap_ppm": "C720x137", "tridiag": "C720x137",
 }  # fmt: skip

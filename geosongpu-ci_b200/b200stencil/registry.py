@@ -107,6 +107,7 @@ def _install_builtin() -> None:
     register("pe_prefix", stencils.pe_prefix)
     register("remap", stencils.remap)
     register("remap_delp", stencils.remap_delp)
+    register("remap_ppm", stencils.remap_ppm)
     register("tridiag", stencils.tridiag)
 
 

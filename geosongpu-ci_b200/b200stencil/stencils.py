@@ -124,6 +124,17 @@ def remap_delp(delp, ptop: float, q1, pe2, q2, stream=None) -> None:
     )  # fmt: skip
 
 
+def remap_ppm(pe1, q1, pe2, q2, kord: int = 4, iv: int = 1, stream=None) -> None:
+    """S6d FV3-style PPM remap (spec: oracle/numpy_oracle.py ppm_profile + remap_ppm_column) -- csrc/k_remap_ppm.cu.
+
+    ``kord`` 4 | 5 | 6: interior limiter (monotone | positive definite | none); ``iv`` 0 for positive
+    definite scalars, 1 otherwise.  Edges must be strictly increasing with ``pe2`` inside ``pe1``."""
+    ni, nj, nk1, nb = shape3(q1)
+    nk2 = shape3(q2)[2]
+    _abi.call("remap_ppm", _abi.precision_of(q1),
+              dict(ni=ni, nj=nj, nk1=nk1, nk2=nk2, nb=nb, kord=int(kord), iv=int(iv), pe1=pe1, q1=q1, pe2=pe2, q2=q2), stream)
+
+
 def tridiag(a, b, c, d, x, w=None, stream=None) -> None:
     """S6c (spec: oracle/numpy_oracle.py tridiag) -- K6c; ``w`` is scratch shaped like ``x``."""
     ni, nj, nk, nb = shape3(b)

@@ -37,6 +37,9 @@ template <typename T>
 int remap_delp(int ni, int nj, int nk1, int nk2, int nb, T ptop, F3<const T> delp, F3<const T> q1, F3<const T> pe2,
                F3<T> q2, cudaStream_t s);
 template <typename T>
+int remap_ppm(int ni, int nj, int nk1, int nk2, int nb, int kord, int iv, F3<const T> pe1, F3<const T> q1,
+              F3<const T> pe2, F3<T> q2, cudaStream_t s);
+template <typename T>
 int tridiag(int ni, int nj, int nk, int nb, F3<const T> a, F3<const T> b, F3<const T> c, F3<const T> d, F3<T> w,
             F3<T> x, cudaStream_t s);
 

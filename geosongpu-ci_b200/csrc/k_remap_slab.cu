@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(32 * NW * CG, MINB) k_remap_slab(const __grid_
   const int64_t sk2 = P.pe2.sk, sko = P.q2.sk;
   const T* e2 = P.pe2.at(valid ? i : 0, j, k2b, b);
   T* o2 = P.q2.at(valid ? i : 0, j, k2b, b);
-  int nlev = valid ? min(CH, nk2 - k2b) : 0;  // target levels of this chunk (<= 0: none)
+  int nlev = valid ? min(CH, nk2 - k2b) : -1;  // target levels of this chunk (<= 0: none; < 0: no edge is loaded either)
   T tgt[CH + 1];
   {
     const T* p = e2;
@@ -281,7 +281,7 @@ int remap_slab(int variant, int ni, int nj, int nk1, int nk2, int nb, T ptop, F3
   const char* what = DELP ? "remap_delp" : "remap";
   int nw = option("remap_nw", 0), cg = option("remap_cg", 0);
   if (variant != 3) nw = 8, cg = 1;
-  if (cg == 0) cg = sizeof(T) == 4 ? 2 : 1;
+  if (cg == 0) cg = 1;  // 32-column CTAs win for both precisions (profiles/r01_remap_geometry.json)
   if (cg == 2 && ni <= 32) cg = 1;
   if (nw == 0) nw = 8;
   if (cg == 2) nw = 8;

@@ -28,6 +28,8 @@ static std::map<std::string, int> g_options = {
     {"remap_variant", 0},   // 0 auto, 1 nested (thread per column), 2 slab + cp.async, 3 slab + TMA (k_remap_slab.cu)
     {"remap_nw", 0},        // slab kernel: warps per column group, 0 auto, 8 | 16
     {"remap_cg", 0},        // slab kernel: 32-column groups per CTA, 0 auto (1 for fp64, 2 for fp32), 1 | 2
+    {"remap_ppm_cols", 0},  // remap_ppm: columns per CTA, 0 auto, 16 | 32 (k_remap_ppm.cu)
+    {"remap_ppm_loader", 0},// remap_ppm: 0 auto, 1 cp.async, 2 TMA
     {"sat_unroll", 0},      // levels per load batch of k_saturation_adjust: 0 auto, 1 | 2 | 4
     {"sat_kchunk", 0},      // levels per thread of k_saturation_adjust: 0 auto (8)
 };

@@ -129,6 +129,11 @@ class COracle:
         nk2 = q2.shape[2]
         self._fn("remap", q1)(_INT(ni), _INT(nj), _INT(nk1), _INT(nk2), *_f3(pe1), *_f3(q1), *_f3(pe2), *_f3(q2))
 
+    def remap_ppm(self, pe1, q1, pe2, q2, kord=4, iv=1):
+        ni, nj, nk1 = q1.shape
+        nk2 = q2.shape[2]
+        self._fn("remap_ppm", q1)(_INT(ni), _INT(nj), _INT(nk1), _INT(nk2), _INT(kord), _INT(iv), *_f3(pe1), *_f3(q1), *_f3(pe2), *_f3(q2))
+
     def tridiag(self, a, b, c, d, x, w=None):
         ni, nj, nk = b.shape
         if w is None:

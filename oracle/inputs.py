@@ -153,6 +153,25 @@ def vertical_inputs(ni, nj, nk, dtype=np.float64, cfg=5, nk2=None, ptop=1.0):
     }
 
 
+def ppm_inputs(ni, nj, nk, dtype=np.float64, cfg=7, nk2=None, smooth=True, positive=True):
+    """Inputs of the PPM remap: the edges of :func:`vertical_inputs`; q1 either a smooth profile in pressure
+    (two sines with column-dependent phase, plus 2 % noise so that limiters fire in places) or pure noise
+    (every layer an extremum: the limiters flatten everything).  ``positive=False`` shifts the tracer so that
+    it changes sign (the positive-definite limiter must then leave it alone where fmin >= 0 does not matter)."""
+    v = vertical_inputs(ni, nj, nk, dtype, cfg=cfg, nk2=nk2)
+    rng = rng_for(cfg + 100)
+    pe1 = v["pe1"].astype(np.float64)
+    pm = 0.5 * (pe1[:, :, 1:] + pe1[:, :, :-1]) / pe1[:, :, -1:]
+    ph = rng.uniform(0, 2 * np.pi, (ni, nj, 1))
+    if smooth:
+        q = 1.0 + 0.6 * np.sin(2 * np.pi * pm + ph) + 0.3 * np.sin(7 * np.pi * pm * pm - ph) + 0.02 * rng.standard_normal((ni, nj, nk))
+        q = np.maximum(q, 0.0) if positive else q - 1.0
+    else:
+        q = rng.uniform(0.0 if positive else -1.0, 1.0, (ni, nj, nk))
+    v["q1"] = as_ifirst(q.astype(dtype))
+    return v
+
+
 def tridiag_inputs(ni, nj, nk, dtype=np.float64, cfg=6):
     """Diagonally dominant system: b = 2 + U(0,1), a, c = -U(0,1) (a[0] = c[nk-1] = 0), d = U(-1,1)."""
     rng = rng_for(cfg)

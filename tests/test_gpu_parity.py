@@ -480,6 +480,96 @@ def test_remap_tall_columns_fall_back(st, remap_variant):
 
 
 
+# ---- S6d PPM remap ---------------------------------------------------------------------
+
+
+@pytest.fixture
+def ppm_options():
+    from b200stencil import _abi
+
+    def force(cols=0, loader=0):
+        _abi.set_option("remap_ppm_cols", cols)
+        _abi.set_option("remap_ppm_loader", loader)
+
+    yield force
+    force()
+
+
+@pytest.mark.parametrize("shape", [(3, 3, 4, 4), (40, 9, 72, 75), (70, 5, 137, 150), (33, 4, 20, 90), (17, 6, 100, 30), (96, 2, 137, 137), (5, 3, 5, 9)])
+@pytest.mark.parametrize("kord,iv", [(4, 1), (4, 0), (5, 0), (5, 1), (6, 1)])
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_remap_ppm(st, corc, ppm_options, shape, kord, iv, dtype):
+    """FV3-style PPM remap against the oracle: every limiter, 16- and 32-column CTAs, TMA and cp.async loaders.
+    The kernel forms reciprocals by Newton iteration, so parity is to the stated tolerance, not bit for bit."""
+    ni, nj, nk, nk2 = shape
+    for smooth in (True, False):
+        v = gen.ppm_inputs(ni, nj, nk, dtype, nk2=nk2, smooth=smooth, positive=(iv == 0))
+        ref = zeros_like_np((ni, nj, nk2), dtype)
+        corc.remap_ppm(v["pe1"], v["q1"], v["pe2"], ref, kord, iv)
+        for cols, loader in ((0, 0), (16, 2), (32, 2), (16, 1), (32, 1)):
+            ppm_options(cols, loader)
+            q2 = up(np.full((ni, nj, nk2), -7.0, dtype))
+            st.remap_ppm(up(v["pe1"]), up(v["q1"]), up(v["pe2"]), q2, kord=kord, iv=iv)
+            assert_close(down(q2), ref, RTOL[dtype], f"q2 cols={cols} loader={loader} smooth={smooth}")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_remap_ppm_unaligned_and_batched(st, corc, ppm_options, dtype):
+    """Interior windows of halo-padded storage (fields start off a 16-byte boundary: shifted TMA boxes), a batch
+    of sub-domains in one launch, and row strides TMA cannot describe (cp.async loader; forcing TMA fails loudly)."""
+    from b200stencil import _abi, fields
+
+    ni, nj, nk, nk2, nb = 45, 7, 72, 72, 3
+    vs = [gen.ppm_inputs(ni, nj, nk, dtype, cfg=7 + b, nk2=nk2) for b in range(nb)]
+    refs = []
+    for v in vs:
+        r = zeros_like_np((ni, nj, nk2), dtype)
+        corc.remap_ppm(v["pe1"], v["q1"], v["pe2"], r, 4, 1)
+        refs.append(r)
+
+    def padded(name, levels, hh):
+        big = fields.zeros((ni + 2 * hh, nj + 2 * hh, levels), dtype=tdt(dtype), batch=nb)
+        win = big[:, hh:hh + ni, hh:hh + nj, :]
+        for b, v in enumerate(vs):
+            win[b].copy_(torch.from_numpy(np.ascontiguousarray(v[name])))
+        return win
+
+    pe1, q1, pe2 = padded("pe1", nk + 1, 3), padded("q1", nk, 1), padded("pe2", nk2 + 1, 3)
+    assert pe1.data_ptr() % 16 != 0 and q1.data_ptr() % 16 != 0
+    for cols, loader in ((0, 0), (16, 2), (32, 2), (32, 1)):
+        ppm_options(cols, loader)
+        q2 = fields.zeros((ni, nj, nk2), dtype=tdt(dtype), batch=nb)
+        st.remap_ppm(pe1, q1, pe2, q2)
+        for b in range(nb):
+            assert_close(down(q2[b]), refs[b], RTOL[dtype], f"batch {b} cols={cols} loader={loader}")
+    v = vs[0]
+    odd = [up(v[n], align_rows=False) for n in ("pe1", "q1", "pe2")]
+    assert odd[0].stride(1) % 2 == 1
+    ppm_options(0, 0)
+    q2 = up(np.zeros((ni, nj, nk2), dtype))
+    st.remap_ppm(*odd, q2)
+    assert_close(down(q2), refs[0], RTOL[dtype], "odd row stride")
+    ppm_options(0, 2)
+    with pytest.raises(_abi.B200StencilError):
+        st.remap_ppm(*odd, q2)
+
+
+def test_remap_ppm_argument_errors(st):
+    from b200stencil import _abi
+
+    v = gen.ppm_inputs(4, 3, 3, np.float64)  # three source layers: the profile needs four
+    with pytest.raises(_abi.B200StencilError) as e:
+        st.remap_ppm(up(v["pe1"]), up(v["q1"]), up(v["pe2"]), up(np.zeros((4, 3, 3))))
+    assert "4 source layers" in str(e.value) or "fewer than 4" in str(e.value)
+    v = gen.ppm_inputs(4, 3, 8, np.float64)
+    with pytest.raises(_abi.B200StencilError):
+        st.remap_ppm(up(v["pe1"]), up(v["q1"]), up(v["pe2"]), up(np.zeros((4, 3, 8))), kord=9)
+    tall = gen.ppm_inputs(2, 2, 900, np.float64)
+    with pytest.raises(_abi.B200StencilError) as e:
+        st.remap_ppm(up(tall["pe1"]), up(tall["q1"]), up(tall["pe2"]), up(np.zeros((2, 2, 900))))
+    assert "shared-memory" in str(e.value)
+
+
 # ---- error channel ---------------------------------------------------------------------------------------
 
 

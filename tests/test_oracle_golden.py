@@ -214,3 +214,62 @@ def test_vertical_numpy_vs_c(corc, shape, dtype):
     r[:, :, 1:] += t["a"][:, :, 1:] * xa[:, :, :-1]
     r[:, :, :-1] += t["c"][:, :, :-1] * xa[:, :, 1:]
     assert np.allclose(r, t["d"], atol=1e-12 if dtype == np.float64 else 1e-4)
+
+
+# ---- S6d PPM remap -----------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("shape", [(3, 3, 4, 4), (6, 5, 20, 23), (5, 3, 72, 60), (4, 2, 137, 137), (4, 2, 5, 9)])
+@pytest.mark.parametrize("kord,iv", [(4, 1), (4, 0), (5, 1), (5, 0), (6, 1), (6, 0)])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_remap_ppm_numpy_vs_c(corc, shape, kord, iv, dtype):
+    """The two restatements of the PPM remap agree bit for bit (both built without FP contraction)."""
+    ni, nj, nk, nk2 = shape
+    for smooth in (True, False):
+        v = gen.ppm_inputs(ni, nj, nk, dtype, nk2=nk2, smooth=smooth, positive=(iv == 0))
+        a, b = zeros_ifirst((ni, nj, nk2), dtype), zeros_ifirst((ni, nj, nk2), dtype)
+        orc.remap_ppm(v["pe1"], v["q1"], v["pe2"], a, kord, iv)
+        corc.remap_ppm(v["pe1"], v["q1"], v["pe2"], b, kord, iv)
+        assert np.isfinite(a).all() and np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("kord,iv", [(4, 1), (5, 0), (6, 1)])
+def test_remap_ppm_properties(corc, kord, iv):
+    ni, nj, nk, nk2 = 8, 6, 72, 80
+    v = gen.ppm_inputs(ni, nj, nk, np.float64, nk2=nk2, positive=True)
+    q2 = zeros_ifirst((ni, nj, nk2), np.float64)
+    corc.remap_ppm(v["pe1"], v["q1"], v["pe2"], q2, kord, iv)
+    dp1, dp2 = np.diff(v["pe1"], axis=2), np.diff(v["pe2"], axis=2)
+    # conservative: the integral of the parabolas over the column is the integral of the means
+    assert np.allclose((q2 * dp2).sum(2), (v["q1"] * dp1).sum(2), rtol=1e-13)
+    # identity: remapping onto the source grid returns the means (each target layer = one whole parabola)
+    same = zeros_ifirst((ni, nj, nk), np.float64)
+    corc.remap_ppm(v["pe1"], v["q1"], v["pe1"], same, kord, iv)
+    assert np.allclose(same, v["q1"], rtol=1e-12, atol=1e-13)
+    # every parabola of the monotone scheme stays between its neighbours' means in the interior
+    al, ar, a6 = orc.ppm_profile(v["q1"], dp1, kord, iv)
+    assert np.allclose(a6, 3.0 * (2.0 * v["q1"] - (al + ar)), rtol=1e-9, atol=1e-12)  # what the CUDA kernel relies on
+    if kord == 4:
+        lo = np.minimum(np.minimum(v["q1"][:, :, :-2], v["q1"][:, :, 1:-1]), v["q1"][:, :, 2:])
+        hi = np.maximum(np.maximum(v["q1"][:, :, :-2], v["q1"][:, :, 1:-1]), v["q1"][:, :, 2:])
+        for edge in (al[:, :, 1:-1], ar[:, :, 1:-1]):
+            assert (edge[:, :, 1:-1] >= lo[:, :, 1:-1] - 1e-12).all() and (edge[:, :, 1:-1] <= hi[:, :, 1:-1] + 1e-12).all()
+    if iv == 0:
+        assert (q2 >= -1e-12).all()  # positive definite in, positive definite out
+
+
+def test_remap_ppm_beats_piecewise_constant_on_a_smooth_profile(corc):
+    """Remap a smooth function of pressure there and back: the PPM round trip must lose far less than the
+    piecewise-constant remap (S6b) does -- the reason the dycore uses it."""
+    ni, nj, nk = 4, 3, 72
+    v = gen.vertical_inputs(ni, nj, nk, np.float64, nk2=nk)
+    pe1, pe2 = v["pe1"], v["pe2"]
+    # f(p) = 1 + 0.5 sin(3 pi p / ps), F = its integral
+    F = lambda p: p - 0.5 * pe1[:, :, -1:] / (3.0 * np.pi) * np.cos(3.0 * np.pi * p / pe1[:, :, -1:])  # noqa: E731
+    q1 = gen.as_ifirst(np.diff(F(pe1), axis=2) / np.diff(pe1, axis=2))  # exact layer means
+    exact2 = np.diff(F(pe2), axis=2) / np.diff(pe2, axis=2)
+    ppm, pcm = zeros_ifirst((ni, nj, nk), np.float64), zeros_ifirst((ni, nj, nk), np.float64)
+    corc.remap_ppm(pe1, q1, pe2, ppm, 4, 1)
+    corc.remap(pe1, q1, pe2, pcm)
+    e_ppm, e_pcm = np.abs(ppm - exact2)[:, :, 3:-3].max(), np.abs(pcm - exact2)[:, :, 3:-3].max()
+    assert e_ppm < 0.2 * e_pcm, (e_ppm, e_pcm)  # measured: 1.4e-3 vs 1.5e-2 on layers of random thickness
