@@ -179,10 +179,10 @@ def prepare(fn_name: str, precision: str, values: Dict[str, Any],
             args.append(v)
             continue
         ctype = a.element_ctype(precision)
-        if v is None:
-            if (a.dims or 1) != 1:
-                raise ValueError(f"{symbol}: field {a.name} is required")
+        if v is None:  # optional output: NULL pointer (zero strides); the library rejects a NULL required field
             args.append(ffi.NULL)
+            if (a.dims or 1) != 1:
+                args += [0] * (3 if a.dims == 3 else 2)
             continue
         if not isinstance(v, torch.Tensor) or not v.is_cuda:
             raise TypeError(f"{symbol}: {a.name} must be a torch CUDA tensor (device storage only, no CPU path)")

@@ -153,6 +153,22 @@ def make(stencil: str, tiles: int, n: int, nk: int, dtype=torch.float64, seed: i
             sets.append((q, crx, xfx, cry, yfx, rarea, fields.empty(shp3, dtype, batch=tiles)))
         return Workload(name, stencil, pts, bpp, lambda s: stencils.fv_tp2d(*sets[s]), ns, keep=sets)
 
+    if stencil == "fv_tp2d_split":  # FV3 fv_tp_2d: q, crx, xfx, cry, yfx in (+ area, rarea IJ); q_out out
+        bpp = 6 * es + 2 * es / nk
+        ns = slots or _slots_for(pts * bpp, cap=4)
+        sets = []
+        for _ in range(ns):
+            q = _rand((ni + 6, nj + 6, nk), dtype, tiles, 0.5, 1.5, g)
+            crx = _rand((ni + 1, nj + 6, nk), dtype, tiles, -0.45, 0.45, g)
+            cry = _rand((ni + 6, nj + 1, nk), dtype, tiles, -0.45, 0.45, g)
+            xfx = _rand((ni + 1, nj + 6, nk), dtype, tiles, 0.9, 1.1, g).mul_(crx)
+            yfx = _rand((ni + 6, nj + 1, nk), dtype, tiles, 0.9, 1.1, g).mul_(cry)
+            area = _rand((ni + 6, nj + 6), dtype, tiles, 0.9, 1.1, g)
+            rarea = fields.empty(shp2, dtype, batch=tiles)
+            rarea[...] = 1.0 / area[:, 3:3 + ni, 3:3 + nj]
+            sets.append((q, crx, xfx, cry, yfx, area, rarea, fields.empty(shp3, dtype, batch=tiles)))
+        return Workload(name, stencil, pts, bpp, lambda s: stencils.fv_tp2d_split(*sets[s]), ns, keep=sets)
+
     if stencil == "remap_delp":  # pe_prefix fused into the remap: delp, q1, pe2 in; q2 out
         bpp = 4 * es
         ns = slots or _slots_for(pts * bpp)
@@ -229,12 +245,12 @@ def make(stencil: str, tiles: int, n: int, nk: int, dtype=torch.float64, seed: i
 
 ALL_STENCILS = [
     "top_of_column", "while_in_function", "hybrid_index_2dout", "find_klcl", "saturation_adjust", "cloud_top",
-    "fv_tp2d", "pe_prefix", "remap", "remap_delp", "remap_ppm", "tridiag",
+    "fv_tp2d", "fv_tp2d_split", "pe_prefix", "remap", "remap_delp", "remap_ppm", "tridiag",
 ]  # fmt: skip
 
 # stencil -> BASELINE config it is quoted on
 DEFAULT_CONFIG: Dict[str, str] = {
     "top_of_column": "C96x72", "while_in_function": "C96x72", "hybrid_index_2dout": "C96x72",
     "find_klcl": "C180x72", "saturation_adjust": "C180x72", "cloud_top": "C180x72",
-    "fv_tp2d": "C384x72", "pe_prefix": "C720x137", "remap": "C720x137", "remap_delp": "C720x137", "remap_ppm": "C720x137", "tridiag": "C720x137",
+    "fv_tp2d": "C384x72", "fv_tp2d_split": "C384x72", "pe_prefix": "C720x137", "remap": "C720x137", "remap_delp": "C720x137", "remap_ppm": "C720x137", "tridiag": "C720x137",
 }  # fmt: skip

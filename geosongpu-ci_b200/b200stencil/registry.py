@@ -105,6 +105,7 @@ def _install_builtin() -> None:
     register("cloud_top", stencils.cloud_top)
     register("fv_tp2d", stencils.fv_tp2d)
     register("pe_prefix", stencils.pe_prefix)
+    register("fv_tp2d_split", stencils.fv_tp2d_split)
     register("remap", stencils.remap)
     register("remap_delp", stencils.remap_delp)
     register("remap_ppm", stencils.remap_ppm)

@@ -29,6 +29,11 @@ int fv_tp2d(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j1, F3<c
             F3<const T> xfx, F3<const T> cry, F3<const T> yfx, F2<const T> rarea, F3<T> q_out, cudaStream_t s);
 
 template <typename T>
+int fv_tp2d_split(int ni, int nj, int nk, int nb, F3<const T> q, F3<const T> crx, F3<const T> xfx, F3<const T> cry,
+                  F3<const T> yfx, F2<const T> area, F2<const T> rarea, F3<T> q_out, F3<T> fx_out, F3<T> fy_out,
+                  cudaStream_t s);
+
+template <typename T>
 int pe_prefix(int ni, int nj, int nk, int nb, T ptop, F3<const T> delp, F3<T> pe, cudaStream_t s);
 template <typename T>
 int remap(int ni, int nj, int nk1, int nk2, int nb, F3<const T> pe1, F3<const T> q1, F3<const T> pe2, F3<T> q2,

@@ -361,12 +361,16 @@ int launch_ppm(const CUtensorMap& me, const CUtensorMap& mq, const PpmParams<T>&
 template <typename T, int COLS>
 int dispatch_ppm(int loader, const CUtensorMap& me, const CUtensorMap& mq, const PpmParams<T>& P, int nj, int nb,
                  cudaStream_t s) {
+  // chunk length CH: the smallest of 5 | 9 | 18 whose NCHUNK chunks cover the column in one round
+  // (16-column CTAs have 16 chunks: CH = 5 for nk2 <= 80, 9 for nk2 <= 144; 32-column CTAs have 8)
   constexpr int NCHUNK = 8 * (32 / COLS);
-  const bool small = P.nk2 <= NCHUNK * 9;
+  const int ch = P.nk2 <= NCHUNK * 5 ? 5 : (P.nk2 <= NCHUNK * 9 ? 9 : 18);
 #define B2S_PPM(CH, LOADER) launch_ppm<T, COLS, CH, LOADER, 2>(me, mq, P, nj, nb, s)
-  if (loader == 0) return small ? B2S_PPM(9, 0) : B2S_PPM(18, 0);
-  if (loader == 2) return small ? B2S_PPM(9, 2) : B2S_PPM(18, 2);
-  return small ? B2S_PPM(9, 1) : B2S_PPM(18, 1);
+#define B2S_PPM_CH(LOADER) (ch == 5 ? B2S_PPM(5, LOADER) : (ch == 9 ? B2S_PPM(9, LOADER) : B2S_PPM(18, LOADER)))
+  if (loader == 0) return B2S_PPM_CH(0);
+  if (loader == 2) return B2S_PPM_CH(2);
+  return B2S_PPM_CH(1);
+#undef B2S_PPM_CH
 #undef B2S_PPM
 }
 
@@ -394,7 +398,9 @@ int remap_ppm(int ni, int nj, int nk1, int nk2, int nb, int kord, int iv, F3<con
   const bool shifted = tma && (fe.off != 0 || fq.off != 0);
   auto bytes = [&](int c) { return (size_t)PpmLayout(nk1, (c + (shifted ? V : 0)) * (int)sizeof(T)).total + 1024; };
   int cols = option("remap_ppm_cols", 0);
-  if (cols != 16 && cols != 32) cols = 3 * bytes(32) <= (size_t)227 * 1024 ? 32 : 16;
+  // measured (profiles/r01_remap_ppm.md): what matters is the chunk each thread marches, not the CTA count --
+  // 32 columns (8 chunks) when 9-level chunks cover the target column, else 16 columns (16 chunks)
+  if (cols != 16 && cols != 32) cols = (nk2 <= 72 && 2 * bytes(32) <= (size_t)227 * 1024) ? 32 : 16;
   if (bytes(cols) > (size_t)227 * 1024 && cols == 32) cols = 16;
   if (bytes(cols) > (size_t)227 * 1024)
     return set_error(B2S_EUNSUPPORTED, "remap_ppm: %d source levels do not fit the shared-memory slabs (limit %d)", nk1,

@@ -131,6 +131,25 @@ def fv_inputs(ni, nj, nk, dtype=np.float64, cfg=4, halo=3):
 # ---- cfg5: vertical scans ---------------------------------------------------------------
 
 
+def fv_split_inputs(ni, nj, nk, dtype=np.float64, cfg=8):
+    """Inputs of fv_tp2d_split: q with a full 3-cell halo (corners included), Courant numbers and area fluxes
+    on the halo-extended interface sets, cell areas with halo.  xfx = crx * dy * dx-ish so that the advected
+    areas ra_x = area + xfx[i] - xfx[i+1] stay well away from zero (|c| <= 0.45 per direction)."""
+    rng = rng_for(cfg)
+    h = 3
+    i = np.arange(-h, ni + h)[:, None, None]
+    j = np.arange(-h, nj + h)[None, :, None]
+    q = 1.0 + 0.5 * np.sin(2 * np.pi * i / max(ni, 1)) * np.cos(2 * np.pi * j / max(nj, 1)) + 0.01 * rng.standard_normal((ni + 2 * h, nj + 2 * h, nk))
+    area = rng.uniform(0.9, 1.1, (ni + 2 * h, nj + 2 * h))
+    crx = rng.uniform(-0.45, 0.45, (ni + 1, nj + 2 * h, nk))
+    cry = rng.uniform(-0.45, 0.45, (ni + 2 * h, nj + 1, nk))
+    xfx = crx * rng.uniform(0.9, 1.1, crx.shape)
+    yfx = cry * rng.uniform(0.9, 1.1, cry.shape)
+    rarea = 1.0 / area[h : h + ni, h : h + nj]
+    f = {"q": q, "crx": crx, "xfx": xfx, "cry": cry, "yfx": yfx, "area": area, "rarea": rarea}
+    return {k: as_ifirst(v.astype(dtype)) for k, v in f.items()}
+
+
 def vertical_inputs(ni, nj, nk, dtype=np.float64, cfg=5, nk2=None, ptop=1.0):
     """delp = U(0.5,1.5) 1000e2/nk; pe1 = ptop + cumsum(delp); pe2 = uniform levels between ptop and pe1[nk]."""
     rng = rng_for(cfg)

@@ -251,6 +251,76 @@ def fv_tp2d(
     q_out[:, :, :] = q[h : h + ni, h : h + nj, :] - rarea[:, :, None] * div
 
 
+def _xppm(q, c):
+    """Unlimited-PPM x-fluxes: q [ni+6, nj, nk] (3-cell halo in i), c [ni+1, nj, nk] -> [ni+1, nj, nk]."""
+    n = c.shape[0]
+    return _ppm_flux(q[0:n], q[1 : n + 1], q[2 : n + 2], q[3 : n + 3], q[4 : n + 4], q[5 : n + 5], c)
+
+
+def _yppm(q, c):
+    """Unlimited-PPM y-fluxes: q [ni, nj+6, nk] (3-cell halo in j), c [ni, nj+1, nk] -> [ni, nj+1, nk]."""
+    n = c.shape[1]
+    return _ppm_flux(q[:, 0:n], q[:, 1 : n + 1], q[:, 2 : n + 2], q[:, 3 : n + 3], q[:, 4 : n + 4], q[:, 5 : n + 5], c)
+
+
+def fv_tp2d_split(
+    q: np.ndarray,
+    crx: np.ndarray,
+    xfx: np.ndarray,
+    cry: np.ndarray,
+    yfx: np.ndarray,
+    area: np.ndarray,
+    rarea: np.ndarray,
+    q_out: np.ndarray,
+    fx_out: np.ndarray = None,
+    fy_out: np.ndarray = None,
+) -> None:
+    """S5b: FV3's fv_tp_2d -- the inner/outer operator splitting of Lin & Rood that
+    removes the directional-splitting error of S5's plain sum of 1-D fluxes.  [recalled] from FV3
+    tp_core.F90 fv_tp_2d with the unlimited PPM of S5 as xppm/yppm; no source in /root/reference.
+
+    q        (ni+6, nj+6, nk)  3-cell halo on every side INCLUDING the corners
+    crx, xfx (ni+1, nj+6, nk)  Courant number / area flux at x-interfaces, rows -3 .. nj+2
+    cry, yfx (ni+6, nj+1, nk)  same at y-interfaces, columns -3 .. ni+2
+    area     (ni+6, nj+6)      cell area with halo;  rarea (ni, nj) its reciprocal on the compute domain
+    q_out    (ni, nj, nk);  fx_out (ni+1, nj, nk), fy_out (ni, nj+1, nk) optional: the averaged fluxes
+
+      fy2 = yppm(q, cry)                         inner y-sweep, every column incl. the i-halo
+      q_i = (q area + yfx fy2 [j] - yfx fy2 [j+1]) / (area + yfx[j] - yfx[j+1])      advected in y
+      fx  = xppm(q_i, crx)                       outer x-sweep on the y-advected field
+      fx2 = xppm(q, crx)                         inner x-sweep, every row incl. the j-halo
+      q_j = (q area + xfx fx2 [i] - xfx fx2 [i+1]) / (area + xfx[i] - xfx[i+1])      advected in x
+      fy  = yppm(q_j, cry)                       outer y-sweep on the x-advected field
+      fx <- 0.5 (fx + fx2) xfx ;  fy <- 0.5 (fy + fy2) yfx
+      q_out = q + rarea (fx[i] - fx[i+1] + fy[j] - fy[j+1])
+    """
+    h = FV_HALO
+    ni, nj, nk = q_out.shape
+    dt = q.dtype.type
+    assert q.shape == (ni + 2 * h, nj + 2 * h, nk) and area.shape == (ni + 2 * h, nj + 2 * h)
+    assert crx.shape == xfx.shape == (ni + 1, nj + 2 * h, nk)
+    assert cry.shape == yfx.shape == (ni + 2 * h, nj + 1, nk)
+    ci, cj = slice(h, h + ni), slice(h, h + nj)
+    a3 = area[:, :, None]
+    fy2 = _yppm(q, cry)  # (ni+6, nj+1, nk)
+    fyy = yfx * fy2
+    ra_y = a3[:, cj] + (yfx[:, :-1] - yfx[:, 1:])
+    q_i = (q[:, cj] * a3[:, cj] + (fyy[:, :-1] - fyy[:, 1:])) / ra_y  # (ni+6, nj, nk)
+    fx = _xppm(q_i, crx[:, cj])  # (ni+1, nj, nk)
+    fx2 = _xppm(q, crx)  # (ni+1, nj+6, nk)
+    fxx = xfx * fx2
+    ra_x = a3[ci] + (xfx[:-1] - xfx[1:])
+    q_j = (q[ci] * a3[ci] + (fxx[:-1] - fxx[1:])) / ra_x  # (ni, nj+6, nk)
+    fy = _yppm(q_j, cry[ci])  # (ni, nj+1, nk)
+    fx = dt(0.5) * (fx + fx2[:, cj]) * xfx[:, cj]
+    fy = dt(0.5) * (fy + fy2[ci]) * yfx[ci]
+    q_out[:, :, :] = q[ci, cj] + rarea[:, :, None] * ((fx[:-1] - fx[1:]) + (fy[:, :-1] - fy[:, 1:]))
+    if fx_out is not None:
+        fx_out[:, :, :] = fx
+    if fy_out is not None:
+        fy_out[:, :, :] = fy
+
+
 # --------------------------------------------------------------------------------------
 # S6  vertical column scans of the dycore.  No reference source: this is the spec
 #     (SURVEY.md 8a S6; field names delp/pe from example_def_dycore.yaml:52-58).

@@ -315,6 +315,73 @@ def test_fv_tp2d_batched(st, corc, dtype):
         assert_close(down(out[b]), ref, RTOL[dtype], f"q_out[{b}]")
 
 
+# ---- S5b fv_tp2d_split -------------------------------------------------------------------
+
+
+def _split_call(st, f, nk, dtype, fluxes=True, ti=0, batch=None):
+    from b200stencil import _abi
+
+    ni, nj = (f["rarea"][0] if batch else f["rarea"]).shape[-2:]
+    d = {k: (up_batch(v) if batch else up(v)) for k, v in f.items()}
+    shp = lambda s: up_batch([np.zeros(s, dtype)] * batch) if batch else up(np.zeros(s, dtype))  # noqa: E731
+    out = shp((ni, nj, nk))
+    fx = shp((ni + 1, nj, nk)) if fluxes else None
+    fy = shp((ni, nj + 1, nk)) if fluxes else None
+    _abi.set_option("fv_split_ti", ti)
+    try:
+        st.fv_tp2d_split(d["q"], d["crx"], d["xfx"], d["cry"], d["yfx"], d["area"], d["rarea"], out, fx, fy)
+    finally:
+        _abi.set_option("fv_split_ti", 0)
+    return out, fx, fy
+
+
+@pytest.mark.parametrize("shape", [(3, 3, 4), (12, 9, 3), (33, 17, 2), (130, 9, 2), (64, 20, 3), (257, 5, 1), (1, 1, 1)])
+@pytest.mark.parametrize("ti", [0, 56, 120])
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_fv_tp2d_split(st, corc, shape, ti, dtype):
+    ni, nj, nk = shape
+    f = gen.fv_split_inputs(ni, nj, nk, dtype)
+    ref, rfx, rfy = zeros_like_np(shape, dtype), zeros_like_np((ni + 1, nj, nk), dtype), zeros_like_np((ni, nj + 1, nk), dtype)
+    corc.fv_tp2d_split(f["q"], f["crx"], f["xfx"], f["cry"], f["yfx"], f["area"], f["rarea"], ref, rfx, rfy)
+    out, fx, fy = _split_call(st, f, nk, dtype, True, ti)
+    assert_close(down(out), ref, RTOL[dtype], "q_out")
+    assert_close(down(fx), rfx, RTOL[dtype], "fx")
+    assert_close(down(fy), rfy, RTOL[dtype], "fy")
+    out2, _, _ = _split_call(st, f, nk, dtype, False, ti)
+    assert torch.equal(out, out2)  # the flux outputs are optional and do not change the update
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_fv_tp2d_split_batched_and_unaligned(st, corc, dtype):
+    """A batch of sub-domains in one launch, and fields that are interior windows of larger storage (their halo
+    origins start off a 16-byte boundary: every TMA box starts at the aligned column before)."""
+    from b200stencil import fields
+
+    ni, nj, nk, nb = 70, 11, 2, 3
+    fs = [gen.fv_split_inputs(ni, nj, nk, dtype, cfg=8 + b) for b in range(nb)]
+    refs = []
+    for f in fs:
+        r = zeros_like_np((ni, nj, nk), dtype)
+        corc.fv_tp2d_split(f["q"], f["crx"], f["xfx"], f["cry"], f["yfx"], f["area"], f["rarea"], r)
+        refs.append(r)
+    out, _, _ = _split_call(st, {k: [f[k] for f in fs] for k in fs[0]}, nk, dtype, False, 0, batch=nb)
+    for b in range(nb):
+        assert_close(down(out[b]), refs[b], RTOL[dtype], f"batch {b}")
+
+    def window(a, off):
+        big = fields.zeros(tuple(n + 2 * off for n in a.shape[:2]) + a.shape[2:], dtype=tdt(dtype))
+        win = big[off:off + a.shape[0], off:off + a.shape[1]]
+        win.copy_(torch.from_numpy(np.ascontiguousarray(a)))
+        return win
+
+    f = fs[0]
+    d = {k: window(f[k], 1 if k in ("q", "cry") else 3) for k in f}
+    assert d["q"].data_ptr() % 16 != 0
+    o = fields.zeros((ni, nj, nk), dtype=tdt(dtype))
+    st.fv_tp2d_split(d["q"], d["crx"], d["xfx"], d["cry"], d["yfx"], d["area"], d["rarea"], o)
+    assert_close(down(o), refs[0], RTOL[dtype], "unaligned windows")
+
+
 # ---- S6 ------------------------------------------------------------------------------------------------
 
 

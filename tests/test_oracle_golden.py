@@ -273,3 +273,49 @@ def test_remap_ppm_beats_piecewise_constant_on_a_smooth_profile(corc):
     corc.remap(pe1, q1, pe2, pcm)
     e_ppm, e_pcm = np.abs(ppm - exact2)[:, :, 3:-3].max(), np.abs(pcm - exact2)[:, :, 3:-3].max()
     assert e_ppm < 0.2 * e_pcm, (e_ppm, e_pcm)  # measured: 1.4e-3 vs 1.5e-2 on layers of random thickness
+
+
+# ---- S5b fv_tp2d_split: FV3 fv_tp_2d inner/outer splitting ---------------------------------------------
+
+
+@pytest.mark.parametrize("shape", [(12, 9, 3), (3, 3, 4), (33, 17, 2), (1, 1, 1)])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_fv_tp2d_split_numpy_vs_c(corc, shape, dtype):
+    ni, nj, nk = shape
+    f = gen.fv_split_inputs(ni, nj, nk, dtype)
+    a, fa, ga = zeros_ifirst(shape, dtype), zeros_ifirst((ni + 1, nj, nk), dtype), zeros_ifirst((ni, nj + 1, nk), dtype)
+    b, fb, gb = zeros_ifirst(shape, dtype), zeros_ifirst((ni + 1, nj, nk), dtype), zeros_ifirst((ni, nj + 1, nk), dtype)
+    orc.fv_tp2d_split(f["q"], f["crx"], f["xfx"], f["cry"], f["yfx"], f["area"], f["rarea"], a, fa, ga)
+    corc.fv_tp2d_split(f["q"], f["crx"], f["xfx"], f["cry"], f["yfx"], f["area"], f["rarea"], b, fb, gb)
+    assert np.array_equal(a, b) and np.array_equal(fa, fb) and np.array_equal(ga, gb)
+    c = zeros_ifirst(shape, dtype)
+    corc.fv_tp2d_split(f["q"], f["crx"], f["xfx"], f["cry"], f["yfx"], f["area"], f["rarea"], c)  # fluxes not requested
+    assert np.array_equal(b, c)
+    # flux form: the update is exactly the divergence of the returned fluxes
+    upd = f["q"][3:-3, 3:-3] + f["rarea"][:, :, None] * ((fa[:-1] - fa[1:]) + (ga[:, :-1] - ga[:, 1:]))
+    assert np.array_equal(upd.astype(dtype), a)
+
+
+def test_fv_tp2d_split_properties(corc):
+    ni, nj, nk = 20, 14, 3
+    f = gen.fv_split_inputs(ni, nj, nk)
+    z = np.zeros_like
+    # a constant field stays constant under non-divergent (here: zero) flow, and takes exactly the flow divergence otherwise
+    out = zeros_ifirst((ni, nj, nk), np.float64)
+    corc.fv_tp2d_split(np.full_like(f["q"], 2.5), z(f["crx"]), z(f["xfx"]), z(f["cry"]), z(f["yfx"]), f["area"], f["rarea"], out)
+    assert np.array_equal(out, np.full_like(out, 2.5))
+    corc.fv_tp2d_split(np.full_like(f["q"], 2.5), f["crx"], f["xfx"], f["cry"], f["yfx"], f["area"], f["rarea"], out)
+    xf, yf = f["xfx"][:, 3:-3], f["yfx"][3:-3]
+    want = 2.5 + f["rarea"][:, :, None] * 2.5 * ((xf[:-1] - xf[1:]) + (yf[:, :-1] - yf[:, 1:]))
+    assert np.allclose(out, want, rtol=1e-13)
+    # with no flow in y the splitting collapses onto the 1-D operator of S5 (q_i = q, fx = fx2): same update as fv_tp2d
+    s5 = zeros_ifirst((ni, nj, nk), np.float64)
+    corc.fv_tp2d(f["q"], gen.as_ifirst(f["crx"][:, 3:-3]), gen.as_ifirst(f["xfx"][:, 3:-3]), gen.as_ifirst(z(f["cry"])[3:-3]),
+                 gen.as_ifirst(z(f["yfx"])[3:-3]), f["rarea"], s5)
+    corc.fv_tp2d_split(f["q"], f["crx"], f["xfx"], z(f["cry"]), z(f["yfx"]), f["area"], f["rarea"], out)
+    assert np.allclose(out, s5, rtol=1e-12, atol=1e-13)
+    # the cross terms are what the splitting adds: with flow in both directions the two operators must differ
+    corc.fv_tp2d(f["q"], gen.as_ifirst(f["crx"][:, 3:-3]), gen.as_ifirst(f["xfx"][:, 3:-3]), gen.as_ifirst(f["cry"][3:-3]),
+                 gen.as_ifirst(f["yfx"][3:-3]), f["rarea"], s5)
+    corc.fv_tp2d_split(f["q"], f["crx"], f["xfx"], f["cry"], f["yfx"], f["area"], f["rarea"], out)
+    assert np.abs(out - s5).max() > 1e-3
