@@ -32,7 +32,33 @@ _FACES = [
     (-_Z, +_Y, +_X),  # tile 6: face -z (south pole)
 ]
 WEST, EAST, SOUTH, NORTH = 0, 1, 2, 3
-EDGE_NAMES = ("west", "east", "south", "north")
+SW, SE, NW, NE = 4, 5, 6, 7  # corner blocks (Link.edge codes), only with corners=True
+EDGE_NAMES = ("west", "east", "south", "north", "south-west", "south-east", "north-west", "north-east")
+
+
+def corner_fill_source(gi: int, gj: int, N: int, direction: int) -> Tuple[int, int]:
+    """FV3's copy_corners ([recalled] fv_mp_mod / tp_core.F90 copy_corners): the halo cell that a cube-corner
+    halo cell (outside the tile in BOTH directions, 0-based tile coordinates) copies, for sweeps in x
+    (direction 1: the row is continued around the corner into the west / east neighbour) or in y (direction 2).
+    The source lies outside the tile in ONE direction only, so it has an owner."""
+    w, s = gi < 0, gj < 0
+    e, n = gi >= N, gj >= N
+    assert (w or e) and (s or n), "not a corner cell"
+    if direction == 1:
+        if w and s:
+            return gj, -gi - 1  # q(i,j) = q(j, 1-i)
+        if e and s:
+            return N - 1 - gj, gi - N  # q(i,j) = q(npy-j, i-npx+1)
+        if e and n:
+            return gj, 2 * N - 1 - gi  # q(i,j) = q(j, 2*npx-1-i)
+        return N - 1 - gj, gi + N  # nw: q(i,j) = q(npy-j, i-1+npx)
+    if w and s:
+        return -gj - 1, gi  # q(i,j) = q(1-j, i)
+    if e and s:
+        return N + gj, N - 1 - gi  # q(i,j) = q(npy+j-1, npx-i)
+    if e and n:
+        return 2 * N - 1 - gj, gi  # q(i,j) = q(2*npy-1-j, i)
+    return gj - N, N - 1 - gi  # nw: q(i,j) = q(j+1-npx, npy-i)
 
 
 def _face(t: int):
@@ -100,8 +126,14 @@ class Link:
 class CubedSpherePartitioner:
     """6 tiles x (lx, ly) sub-domains of an N x N-cell tile; rank = tile*lx*ly + sy*lx + sx."""
 
-    def __init__(self, N: int, layout: Tuple[int, int] = (1, 1), halo: int = 3):
+    def __init__(self, N: int, layout: Tuple[int, int] = (1, 1), halo: int = 3, corners: bool = False):
+        """``corners=True`` adds the four corner blocks of every halo to the links (needed by stencils that
+        sweep twice, S5b fv_tp2d_split): a corner block inside the tile or across ONE tile edge comes from the
+        diagonal neighbour; at the eight cube corners, where no such neighbour exists, it is filled by FV3's
+        copy_corners rule for x-sweeps (direction 1), folded into the link so that it reads the owner's interior
+        directly (one pass, no ordering between edge and corner copies)."""
         lx, ly = layout
+        self.corners = corners
         if N % lx or N % ly:
             raise ValueError(f"layout {layout} does not divide C{N}")
         self.N, self.lx, self.ly, self.halo = N, lx, ly, halo
@@ -125,9 +157,51 @@ class CubedSpherePartitioner:
         sx, sy = i2 // self.nx, j2 // self.ny
         return self.rank_of(t2, sx, sy), i2 - sx * self.nx, j2 - sy * self.ny
 
+    def owner_any(self, t: int, gi: int, gj: int, direction: int = 1) -> Tuple[int, int, int]:
+        """:meth:`owner` extended to cube-corner halo cells through :func:`corner_fill_source`."""
+        N = self.N
+        if not (0 <= gi < N or 0 <= gj < N):
+            gi, gj = corner_fill_source(gi, gj, N, direction)
+        return self.owner(t, gi, gj)
+
+    def cube_corner_flags(self, rank: int) -> int:
+        """Bit mask of the halo corners of ``rank`` that sit at a cube corner: 1 SW, 2 SE, 4 NW, 8 NE."""
+        _, sx, sy = self.subdomain(rank)
+        w, e, s, n = sx == 0, sx == self.lx - 1, sy == 0, sy == self.ly - 1
+        return (1 if w and s else 0) | (2 if e and s else 0) | (4 if w and n else 0) | (8 if e and n else 0)
+
+    def _corner_links(self, rank: int) -> List[Link]:
+        t, sx, sy = self.subdomain(rank)
+        h, nx, ny = self.halo, self.nx, self.ny
+        out: List[Link] = []
+        # (code, first cell, step in depth (i), step along (j)): d runs over i, p over j
+        blocks = [(SW, (-1, -1), (-1, 0), (0, -1)), (SE, (nx, -1), (1, 0), (0, -1)),
+                  (NW, (-1, ny), (-1, 0), (0, 1)), (NE, (nx, ny), (1, 0), (0, 1))]  # fmt: skip
+        for code, (i0, j0), (ddi, ddj), (dpi, dpj) in blocks:
+            src = np.empty((h, h, 3), dtype=np.int64)
+            for d in range(h):
+                for p in range(h):
+                    li, lj = i0 + d * ddi + p * dpi, j0 + d * ddj + p * dpj
+                    src[d, p] = self.owner_any(t, sx * nx + li, sy * ny + lj, 1)
+            dd, pp = np.meshgrid(np.arange(h), np.arange(h), indexing="ij")
+            sd = (src[1, 0, 1:] - src[0, 0, 1:]) if h > 1 else np.zeros(2, dtype=np.int64)
+            sp = (src[0, 1, 1:] - src[0, 0, 1:]) if h > 1 else np.zeros(2, dtype=np.int64)
+            one_owner = np.all(src[:, :, 0] == src[0, 0, 0])
+            affine = one_owner and np.array_equal(src[:, :, 1], src[0, 0, 1] + dd * sd[0] + pp * sp[0]) \
+                and np.array_equal(src[:, :, 2], src[0, 0, 2] + dd * sd[1] + pp * sp[1])
+            if affine:
+                out.append(Link(rank, int(src[0, 0, 0]), code, h, h, i0, j0, ddi, ddj, dpi, dpj,
+                                int(src[0, 0, 1]), int(src[0, 0, 2]), int(sd[0]), int(sd[1]), int(sp[0]), int(sp[1])))  # fmt: skip
+            else:  # a block that straddles two owners (exotic layouts): one link per cell
+                for d in range(h):
+                    for p in range(h):
+                        out.append(Link(rank, int(src[d, p, 0]), code, 1, 1, i0 + d * ddi + p * dpi, j0 + d * ddj + p * dpj,
+                                        0, 0, 0, 0, int(src[d, p, 1]), int(src[d, p, 2]), 0, 0, 0, 0))  # fmt: skip
+        return out
+
     # ---- halo links -------------------------------------------------------------------------------
     def links_into(self, rank: int) -> List[Link]:
-        """Every strip copy that fills the (edge, not corner) halo of ``rank``."""
+        """Every strip copy that fills the edge halo of ``rank`` (and, with ``corners=True``, its corner blocks)."""
         t, sx, sy = self.subdomain(rank)
         h, nx, ny = self.halo, self.nx, self.ny
         out: List[Link] = []
@@ -164,6 +238,8 @@ class CubedSpherePartitioner:
                          si0, sj0, int(sd[0]), int(sd[1]), int(sp[0]), int(sp[1]))
                 )  # fmt: skip
                 p0 = p1
+        if self.corners:
+            out += self._corner_links(rank)
         return out
 
     def all_links(self) -> List[Link]:
@@ -206,17 +282,23 @@ def global_id_field(part: CubedSpherePartitioner, rank: int, nk: int = 1) -> np.
     return f
 
 
-def expected_halo(part: CubedSpherePartitioner, rank: int, nk: int = 1) -> np.ndarray:
-    """What the halo-padded global-id field of ``rank`` must hold after an exchange (corners stay -1)."""
+def expected_halo(part: CubedSpherePartitioner, rank: int, nk: int = 1, direction: int = 1) -> np.ndarray:
+    """What the halo-padded global-id field of ``rank`` must hold after an exchange.  Without ``part.corners`` the
+    corner blocks stay -1; with it they hold the diagonal neighbour's ids, or at a cube corner the ids FV3's
+    copy_corners rule for ``direction`` puts there (the exchange fills direction 1)."""
     t, sx, sy = part.subdomain(rank)
     h, nx, ny, N = part.halo, part.nx, part.ny, part.N
     f = global_id_field(part, rank, nk)
     for li in range(-h, nx + h):
         for lj in range(-h, ny + h):
             inside_i, inside_j = 0 <= li < nx, 0 <= lj < ny
-            if inside_i == inside_j:
-                continue  # interior or corner
+            if inside_i and inside_j:
+                continue
+            if not inside_i and not inside_j and not part.corners:
+                continue
             gi, gj = sx * nx + li, sy * ny + lj
+            if not (0 <= gi < N or 0 <= gj < N):
+                gi, gj = corner_fill_source(gi, gj, N, direction)
             t2, i2, j2 = unfold(t, gi, gj, N)
             f[li + h, lj + h, :] = ((t2 * N + j2) * N + i2) * nk + np.arange(nk)
     return f

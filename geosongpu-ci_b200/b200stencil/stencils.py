@@ -100,20 +100,23 @@ def fv_tp2d(q, crx, xfx, cry, yfx, rarea, q_out, region=None, q_out_halo: int = 
     prepare_fv_tp2d(q, crx, xfx, cry, yfx, rarea, q_out, region, q_out_halo)(stream)
 
 
-def fv_tp2d_split(q, crx, xfx, cry, yfx, area, rarea, q_out, fx_out=None, fy_out=None, stream=None) -> None:
+def fv_tp2d_split(q, crx, xfx, cry, yfx, area, rarea, q_out, fx_out=None, fy_out=None, corner_flags=None, stream=None) -> None:
     """S5b FV3 fv_tp_2d, inner/outer operator splitting (spec: oracle/numpy_oracle.py fv_tp2d_split) -- csrc/k_fv_split.cu.
 
     ``q`` and ``area`` carry a 3-cell halo on every side INCLUDING the corners ([b,] ni+6, nj+6[, nk]); ``crx``/``xfx``
     are ([b,] ni+1, nj+6, nk) (x-interfaces of the rows -3 .. nj+2), ``cry``/``yfx`` ([b,] ni+6, nj+1, nk); ``rarea`` and
     ``q_out`` are compute-domain shaped; ``fx_out`` ([b,] ni+1, nj, nk) / ``fy_out`` ([b,] ni, nj+1, nk) optionally receive
-    the averaged fluxes."""
+    the averaged fluxes.  ``corner_flags`` (int32 device tensor, one entry per sub-domain of the batch; see
+    ``CubedSpherePartitioner.cube_corner_flags``) marks halo corners that are cube corners: the corner cells of ``q``
+    then hold FV3's copy_corners values for x-sweeps (what the halo update writes) and the inner y-sweep takes the
+    direction-2 values from the sub-domain's own south / north halo."""
     h = FV_HALO
     nip, njp, nk, nb = shape3(q)
     ni, nj = nip - 2 * h, njp - 2 * h
     _abi.call(
         "fv_tp2d_split", _abi.precision_of(q),
-        dict(ni=ni, nj=nj, nk=nk, nb=nb, q=q, crx=crx, xfx=xfx, cry=cry, yfx=yfx, area=area, rarea=rarea, q_out=q_out,
-             fx_out=fx_out, fy_out=fy_out),
+        dict(ni=ni, nj=nj, nk=nk, nb=nb, q=q, crx=crx, xfx=xfx, cry=cry, yfx=yfx, area=area, rarea=rarea,
+             corner_flags=corner_flags, q_out=q_out, fx_out=fx_out, fy_out=fy_out),
         stream, origins={"q": (h, h, 0), "area": (h, h), "crx": (0, h, 0), "xfx": (0, h, 0), "cry": (h, 0, 0), "yfx": (h, 0, 0)},
     )  # fmt: skip
 

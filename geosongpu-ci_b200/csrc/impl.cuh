@@ -30,8 +30,8 @@ int fv_tp2d(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j1, F3<c
 
 template <typename T>
 int fv_tp2d_split(int ni, int nj, int nk, int nb, F3<const T> q, F3<const T> crx, F3<const T> xfx, F3<const T> cry,
-                  F3<const T> yfx, F2<const T> area, F2<const T> rarea, F3<T> q_out, F3<T> fx_out, F3<T> fy_out,
-                  cudaStream_t s);
+                  F3<const T> yfx, F2<const T> area, F2<const T> rarea, const int* corner_flags, F3<T> q_out,
+                  F3<T> fx_out, F3<T> fy_out, cudaStream_t s);
 
 template <typename T>
 int pe_prefix(int ni, int nj, int nk, int nb, T ptop, F3<const T> delp, F3<T> pe, cudaStream_t s);

@@ -21,6 +21,10 @@
 //   C  thread = x-interface: outer x-sweep on q_i -> averaged flux fx; thread = column: outer y-sweep
 //      on q_j -> averaged flux fy in registers;
 //   D  thread = column: q_out, streamed to HBM (and fx / fy when the caller wants the fluxes).
+// Cube corners (FV3 copy_corners): the halo-corner cells of q hold the values for x-sweeps (direction 1, filled
+// by the halo update); where `corner_flags[b]` marks a halo corner as a cube corner, the inner y-sweep reads
+// the direction-2 values instead -- a rotated copy of the sub-domain's own south / north halo, fetched
+// straight from global memory by the three apron-column threads concerned.
 // All arithmetic goes through the explicit-rounding helpers of fv_math.cuh; the two divisions per cell are
 // MUFU.RCP64H + two Newton steps in fp64 (<= 1 ulp).  Parity with the oracle: 1e-12 (fp64) / 1e-5 (fp32).
 // Algorithmic bytes/point: 40 R + 8 W (+ 16 W with the flux outputs) + 16/nk for area and rarea.
@@ -76,6 +80,8 @@ struct SplitParams {
   int c_q, c_crx, c_xfx, c_cry, c_yfx;  // TMA coordinate of the first box column of strip 0
   int s_q, s_crx, s_xfx, s_cry, s_yfx;  // elements to skip inside a box row (16-byte alignment shift)
   F2<const T> area, rarea;              // area addresses compute cell (0, 0); its halo sits at negative offsets
+  F3<const T> q;                        // compute cell (0, 0, 0): only read for the direction-2 corner values
+  const int* corner_flags;              // per sub-domain: 1 SW | 2 SE | 4 NW | 8 NE halo corner is a cube corner; may be NULL
   F3<T> qout, fxo, fyo;
 };
 
@@ -144,14 +150,35 @@ __global__ void __launch_bounds__(SplitTile<T, TI, R>::THREADS) k_fv_split(const
   // ---- A: inner y-sweep, thread = column c of the apron-extended tile (compute column i0 - 3 + c) ----
   if (tid < tw + 6) {
     const int c = tid;
+    // q of tile row r in this thread's column as the y-sweep must see it (oracle: copy_corners direction 2)
+    const int flags = P.corner_flags ? __ldg(P.corner_flags + b) : 0;
+    const int ia = i0 - 3 + c;
+    const bool patch = flags != 0 && (ia < 0 || (ia >= P.ni && ia < P.ni + 3));
+    auto qy = [&](int r) -> T {
+      if (patch) {
+        const int j = j0 - 3 + r;
+        if ((j < 0 || j >= P.nj) && j < P.nj + 3) {
+          const int bit = ia < 0 ? (j < 0 ? 1 : 4) : (j < 0 ? 2 : 8);
+          if (flags & bit) {
+            int si, sj;
+            if (bit == 1) si = -j - 1, sj = ia;                                  // SW: q(i,j) = q(1-j, i)
+            else if (bit == 2) si = P.ni + j, sj = P.ni - 1 - ia;                // SE: q(npy+j-1, npx-i)
+            else if (bit == 8) si = P.ni + P.nj - 1 - j, sj = ia - P.ni + P.nj;  // NE: q(2*npy-1-j, i)
+            else si = j - P.nj, sj = P.nj - 1 - ia;                              // NW: q(j+1-npx, npy-i)
+            return __ldg(P.q.at(si, sj, k, b));
+          }
+        }
+      }
+      return qs[r * WQ + c];
+    };
     // window of six q values around interface j0 + r: rows (r .. r+5) of the q tile
-    T w0 = qs[0 * WQ + c], w1 = qs[1 * WQ + c], w2 = qs[2 * WQ + c], w3 = qs[3 * WQ + c], w4 = qs[4 * WQ + c];
+    T w0 = qy(0), w1 = qy(1), w2 = qy(2), w3 = qy(3), w4 = qy(4);
     T al_a = ppm_al(w0, w1, w2, w3);  // low-side interface value of the cell in row r+2 ... advanced below
     T al_b = ppm_al(w1, w2, w3, w4);
     T f_lo = T(0), y_lo = T(0);
 #pragma unroll
     for (int r = 0; r <= R; ++r) {
-      const T w5 = qs[(r + 5) * WQ + c];
+      const T w5 = qy(r + 5);
       const T al_c = ppm_al(w2, w3, w4, w5);
       // interface j0+r lies between rows r+2 (low side) and r+3 (high side) of the tile
       const T f = ppm_flux_from_al(w2, w3, al_a, al_b, al_c, cys[r * WQ + c]);
@@ -252,8 +279,8 @@ __global__ void __launch_bounds__(SplitTile<T, TI, R>::THREADS) k_fv_split(const
 
 template <typename T, int TI, int R>
 int launch_split(int ni, int nj, int nk, int nb, F3<const T> q, F3<const T> crx, F3<const T> xfx, F3<const T> cry,
-                 F3<const T> yfx, F2<const T> area, F2<const T> rarea, F3<T> q_out, F3<T> fxo, F3<T> fyo, cudaStream_t s,
-                 bool* applicable) {
+                 F3<const T> yfx, F2<const T> area, F2<const T> rarea, const int* corner_flags, F3<T> q_out, F3<T> fxo,
+                 F3<T> fyo, cudaStream_t s, bool* applicable) {
   using G = SplitTile<T, TI, R>;
   constexpr int V = G::V;
   *applicable = false;
@@ -295,6 +322,7 @@ int launch_split(int ni, int nj, int nk, int nb, F3<const T> q, F3<const T> crx,
   P.s_cry = fcy.off % V, P.c_cry = fcy.off - P.s_cry;
   P.s_yfx = fyx.off % V, P.c_yfx = fyx.off - P.s_yfx;
   P.area = area, P.rarea = rarea;
+  P.q = q, P.corner_flags = corner_flags;
   P.qout = q_out, P.fxo = fxo, P.fyo = fyo;
   *applicable = true;
   kern<<<(unsigned)nitems, G::THREADS, G::SMEM_BYTES, s>>>(mq, mcx, mxx, mcy, myx, P);
@@ -307,8 +335,8 @@ int launch_split(int ni, int nj, int nk, int nb, F3<const T> q, F3<const T> crx,
 // TI + 6 and TI + 1 threads must fit a whole number of warps (64 and 128 threads)
 template <typename T>
 int fv_tp2d_split(int ni, int nj, int nk, int nb, F3<const T> q, F3<const T> crx, F3<const T> xfx, F3<const T> cry,
-                  F3<const T> yfx, F2<const T> area, F2<const T> rarea, F3<T> q_out, F3<T> fx_out, F3<T> fy_out,
-                  cudaStream_t s) {
+                  F3<const T> yfx, F2<const T> area, F2<const T> rarea, const int* corner_flags, F3<T> q_out,
+                  F3<T> fx_out, F3<T> fy_out, cudaStream_t s) {
   B2S_ARGCHECK(ni > 0 && nj > 0 && nk > 0 && nb > 0, "fv_tp2d_split: empty domain %dx%dx%dx%d", ni, nj, nk, nb);
   B2S_ARGCHECK(q.p && crx.p && xfx.p && cry.p && yfx.p && area.p && rarea.p && q_out.p, "fv_tp2d_split: null field");
   int ti = option("fv_split_ti", 0);
@@ -316,9 +344,9 @@ int fv_tp2d_split(int ni, int nj, int nk, int nb, F3<const T> q, F3<const T> crx
   bool applicable = false;
   int rc;
   if (ti == 120)
-    rc = launch_split<T, 120, 4>(ni, nj, nk, nb, q, crx, xfx, cry, yfx, area, rarea, q_out, fx_out, fy_out, s, &applicable);
+    rc = launch_split<T, 120, 4>(ni, nj, nk, nb, q, crx, xfx, cry, yfx, area, rarea, corner_flags, q_out, fx_out, fy_out, s, &applicable);
   else
-    rc = launch_split<T, 56, 8>(ni, nj, nk, nb, q, crx, xfx, cry, yfx, area, rarea, q_out, fx_out, fy_out, s, &applicable);
+    rc = launch_split<T, 56, 8>(ni, nj, nk, nb, q, crx, xfx, cry, yfx, area, rarea, corner_flags, q_out, fx_out, fy_out, s, &applicable);
   if (applicable) return rc;
   return set_error(B2S_EUNSUPPORTED,
                    "fv_tp2d_split: the fields do not meet the TMA rules (element-aligned pointers, row / level / batch strides "
@@ -327,7 +355,7 @@ int fv_tp2d_split(int ni, int nj, int nk, int nb, F3<const T> q, F3<const T> crx
 
 #define INSTANTIATE(T)                                                                                                   \
   template int fv_tp2d_split<T>(int, int, int, int, F3<const T>, F3<const T>, F3<const T>, F3<const T>, F3<const T>,    \
-                                F2<const T>, F2<const T>, F3<T>, F3<T>, F3<T>, cudaStream_t);
+                                F2<const T>, F2<const T>, const int*, F3<T>, F3<T>, F3<T>, cudaStream_t);
 INSTANTIATE(double)
 INSTANTIATE(float)
 

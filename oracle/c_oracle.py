@@ -120,14 +120,21 @@ class COracle:
             *_f2(rarea), *_f3(q_out),
         )  # fmt: skip
 
-    def fv_tp2d_split(self, q, crx, xfx, cry, yfx, area, rarea, q_out, fx_out=None, fy_out=None):
+    def fv_tp2d_split(self, q, crx, xfx, cry, yfx, area, rarea, q_out, fx_out=None, fy_out=None, corner_flags=0):
+        from . import numpy_oracle
+
         ni, nj, nk = q_out.shape
+        qy = q
+        if corner_flags:  # what the inner y-sweep sees at cube corners (copy_corners direction 2)
+            qy = np.empty(tuple(reversed(q.shape)), dtype=q.dtype).transpose()
+            qy[...] = q
+            numpy_oracle.copy_corners(qy, 2, corner_flags)
         null3 = (_P(None), _I64(0), _I64(0))
         a_it = area.itemsize
         assert area.ndim == 2 and area.strides[0] == a_it
         area_at = (_P(area.ctypes.data + 3 * area.strides[0] + 3 * area.strides[1]), _I64(area.strides[1] // a_it))
         self._fn("fv_tp2d_split", q)(
-            _INT(ni), _INT(nj), _INT(nk), *_f3(q, (3, 3, 0)), *_f3(crx, (0, 3, 0)), *_f3(xfx, (0, 3, 0)),
+            _INT(ni), _INT(nj), _INT(nk), *_f3(q, (3, 3, 0)), *_f3(qy, (3, 3, 0)), *_f3(crx, (0, 3, 0)), *_f3(xfx, (0, 3, 0)),
             *_f3(cry, (3, 0, 0)), *_f3(yfx, (3, 0, 0)), *area_at, *_f2(rarea), *_f3(q_out),
             *(_f3(fx_out) if fx_out is not None else null3), *(_f3(fy_out) if fy_out is not None else null3),
         )  # fmt: skip

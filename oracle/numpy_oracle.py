@@ -263,6 +263,43 @@ def _yppm(q, c):
     return _ppm_flux(q[:, 0:n], q[:, 1 : n + 1], q[:, 2 : n + 2], q[:, 3 : n + 3], q[:, 4 : n + 4], q[:, 5 : n + 5], c)
 
 
+def corner_fill_source_local(li: int, lj: int, ni: int, nj: int, direction: int):
+    """[recalled] FV3 copy_corners, in the 0-based compute coordinates of a sub-domain of ni x nj cells whose halo
+    corner (li, lj) sits at a cube corner: the halo cell whose value the corner cell takes for sweeps in x
+    (direction 1) or y (direction 2).  1-based FV3 forms: SW q(i,j) = q(j,1-i) | q(1-j,i); SE q(npy-j,i-npx+1) |
+    q(npy+j-1,npx-i); NE q(j,2npx-1-i) | q(2npy-1-j,i); NW q(npy-j,i-1+npx) | q(j+1-npx,npy-i)."""
+    w, s = li < 0, lj < 0
+    if direction == 1:
+        if w and s:
+            return lj, -li - 1
+        if not w and s:
+            return ni - 1 - lj, li - ni
+        if not w and not s:
+            return lj - nj + ni, ni + nj - 1 - li
+        return nj - 1 - lj, li + nj
+    if w and s:
+        return -lj - 1, li
+    if not w and s:
+        return ni + lj, ni - 1 - li
+    if not w and not s:
+        return ni + nj - 1 - lj, li - ni + nj
+    return lj - nj, nj - 1 - li
+
+
+def copy_corners(q: np.ndarray, direction: int, flags: int = 15, h: int = FV_HALO) -> None:
+    """Fill, in place, the halo-corner blocks of q [ni+2h, nj+2h(, nk)] marked in ``flags`` (1 SW, 2 SE, 4 NW, 8 NE)
+    from the edge halos, FV3 copy_corners rule for ``direction``."""
+    ni, nj = q.shape[0] - 2 * h, q.shape[1] - 2 * h
+    for bit, irange, jrange in ((1, range(-h, 0), range(-h, 0)), (2, range(ni, ni + h), range(-h, 0)),
+                                (4, range(-h, 0), range(nj, nj + h)), (8, range(ni, ni + h), range(nj, nj + h))):  # fmt: skip
+        if not flags & bit:
+            continue
+        for li in irange:
+            for lj in jrange:
+                si, sj = corner_fill_source_local(li, lj, ni, nj, direction)
+                q[li + h, lj + h] = q[si + h, sj + h]
+
+
 def fv_tp2d_split(
     q: np.ndarray,
     crx: np.ndarray,
@@ -274,6 +311,7 @@ def fv_tp2d_split(
     q_out: np.ndarray,
     fx_out: np.ndarray = None,
     fy_out: np.ndarray = None,
+    corner_flags: int = 0,
 ) -> None:
     """S5b: FV3's fv_tp_2d -- the inner/outer operator splitting of Lin & Rood that
     removes the directional-splitting error of S5's plain sum of 1-D fluxes.  [recalled] from FV3
@@ -293,6 +331,11 @@ def fv_tp2d_split(
       fy  = yppm(q_j, cry)                       outer y-sweep on the x-advected field
       fx <- 0.5 (fx + fx2) xfx ;  fy <- 0.5 (fy + fy2) yfx
       q_out = q + rarea (fx[i] - fx[i+1] + fy[j] - fy[j+1])
+
+    ``corner_flags`` (1 SW | 2 SE | 4 NW | 8 NE): halo corners of this sub-domain that are cube corners.  FV3 calls
+    copy_corners(q, dir=2) before the inner y-sweep and copy_corners(q, dir=1) before the inner x-sweep; here the
+    corner cells of ``q`` already hold the direction-1 values (the halo update writes them) and the y-sweep runs on a
+    copy whose flagged corners are re-filled with the direction-2 rule.
     """
     h = FV_HALO
     ni, nj, nk = q_out.shape
@@ -302,7 +345,11 @@ def fv_tp2d_split(
     assert cry.shape == yfx.shape == (ni + 2 * h, nj + 1, nk)
     ci, cj = slice(h, h + ni), slice(h, h + nj)
     a3 = area[:, :, None]
-    fy2 = _yppm(q, cry)  # (ni+6, nj+1, nk)
+    qy = q
+    if corner_flags:
+        qy = q.copy()
+        copy_corners(qy, 2, corner_flags)
+    fy2 = _yppm(qy, cry)  # (ni+6, nj+1, nk)
     fyy = yfx * fy2
     ra_y = a3[:, cj] + (yfx[:, :-1] - yfx[:, 1:])
     q_i = (q[:, cj] * a3[:, cj] + (fyy[:, :-1] - fyy[:, 1:])) / ra_y  # (ni+6, nj, nk)

@@ -351,6 +351,35 @@ def test_fv_tp2d_split(st, corc, shape, ti, dtype):
     assert torch.equal(out, out2)  # the flux outputs are optional and do not change the update
 
 
+@pytest.mark.parametrize("shape", [(12, 9, 3), (70, 11, 2), (130, 20, 1)])
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_fv_tp2d_split_cube_corners(st, corc, shape, dtype):
+    """Sub-domains at cube corners: q holds the copy_corners direction-1 values (as after a halo update); with the
+    flags set, the kernel's inner y-sweep must use the direction-2 values like the oracle."""
+    ni, nj, nk = shape
+    nb = 4
+    all_flags = [1, 10, 15, 0]
+    fs, refs = [], []
+    for b, flags in enumerate(all_flags):
+        f = gen.fv_split_inputs(ni, nj, nk, dtype, cfg=8 + b)
+        q1 = np.array(f["q"])
+        orc.copy_corners(q1, 1, flags)
+        f["q"] = gen.as_ifirst(q1)
+        r = zeros_like_np((ni, nj, nk), dtype)
+        corc.fv_tp2d_split(f["q"], f["crx"], f["xfx"], f["cry"], f["yfx"], f["area"], f["rarea"], r, corner_flags=flags)
+        fs.append(f)
+        refs.append(r)
+    d = {k: up_batch([f[k] for f in fs]) for k in fs[0]}
+    out = up_batch([np.zeros((ni, nj, nk), dtype)] * nb)
+    cf = torch.tensor(all_flags, dtype=torch.int32, device="cuda")
+    st.fv_tp2d_split(d["q"], d["crx"], d["xfx"], d["cry"], d["yfx"], d["area"], d["rarea"], out, corner_flags=cf)
+    for b in range(nb):
+        assert_close(down(out[b]), refs[b], RTOL[dtype], f"sub-domain {b} flags {all_flags[b]}")
+    plain = up_batch([np.zeros((ni, nj, nk), dtype)] * nb)
+    st.fv_tp2d_split(d["q"], d["crx"], d["xfx"], d["cry"], d["yfx"], d["area"], d["rarea"], plain)
+    assert not torch.equal(plain[0], out[0]) and torch.equal(plain[3], out[3])  # the flags matter, and only where set
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_fv_tp2d_split_batched_and_unaligned(st, corc, dtype):
     """A batch of sub-domains in one launch, and fields that are interior windows of larger storage (their halo

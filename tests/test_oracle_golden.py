@@ -319,3 +319,29 @@ def test_fv_tp2d_split_properties(corc):
                  gen.as_ifirst(f["yfx"][3:-3]), f["rarea"], s5)
     corc.fv_tp2d_split(f["q"], f["crx"], f["xfx"], f["cry"], f["yfx"], f["area"], f["rarea"], out)
     assert np.abs(out - s5).max() > 1e-3
+
+
+@pytest.mark.parametrize("flags", [1, 2, 4, 8, 15, 6])
+def test_fv_tp2d_split_cube_corners(corc, flags):
+    """copy_corners: the y-sweep of a sub-domain at a cube corner sees direction-2 corner values."""
+    ni, nj, nk = 10, 7, 2
+    f = gen.fv_split_inputs(ni, nj, nk)
+    q1 = f["q"].copy()
+    orc.copy_corners(q1, 1, flags)  # what the halo update leaves in q
+    a, b = zeros_ifirst((ni, nj, nk), np.float64), zeros_ifirst((ni, nj, nk), np.float64)
+    q1 = gen.as_ifirst(q1)
+    orc.fv_tp2d_split(q1, f["crx"], f["xfx"], f["cry"], f["yfx"], f["area"], f["rarea"], a, corner_flags=flags)
+    corc.fv_tp2d_split(q1, f["crx"], f["xfx"], f["cry"], f["yfx"], f["area"], f["rarea"], b, corner_flags=flags)
+    assert np.array_equal(a, b)
+    plain = zeros_ifirst((ni, nj, nk), np.float64)
+    orc.fv_tp2d_split(q1, f["crx"], f["xfx"], f["cry"], f["yfx"], f["area"], f["rarea"], plain)
+    diff = np.argwhere(np.abs(plain - a).max(axis=2) > 0)
+    assert len(diff) > 0  # the corner rule matters ...
+    for i, j in diff:  # ... and only within reach (3 cells in i, via q_i) of a flagged corner
+        near = [(i < 3 and j < 6, 1), (i >= ni - 3 and j < 6, 2), (i < 3 and j >= nj - 6, 4), (i >= ni - 3 and j >= nj - 6, 8)]
+        assert any(c and (flags & bit) for c, bit in near), (i, j)
+    # direction-1 and direction-2 fills are each other's transposes about the corner diagonal
+    qx, qy = np.array(f["q"]), np.array(f["q"])
+    orc.copy_corners(qx, 1, 1)
+    orc.copy_corners(qy, 2, 1)
+    assert np.array_equal(qy[2, 2], f["q"][3, 2]) and np.array_equal(qx[2, 2], f["q"][2, 3])  # cell (-1,-1) <- (0,-1) | (-1,0)

@@ -6,7 +6,8 @@ import numpy as np
 import pytest
 import torch
 
-from b200stencil.halo.partitioner import (EAST, NORTH, SOUTH, WEST, CubedSpherePartitioner, layout_for, unfold)
+from b200stencil.halo.partitioner import (EAST, NORTH, SOUTH, WEST, CubedSpherePartitioner, _face, corner_fill_source,
+                                           layout_for, unfold)
 from b200stencil.halo.updater import HaloPlan, HaloUpdater, exchange_in_process
 
 from halo_util import batch_field, check_field, cpu_mover
@@ -76,6 +77,68 @@ def test_links_cover_every_edge_halo_cell_once(layout):
             for cj in (slice(0, h), slice(-h, None)):
                 want[ci, cj] = 0
         assert np.array_equal(seen, want)
+
+
+def _centre(t, i, j, N):
+    """3-D position of the centre of cell (i, j) of tile t on the cube of side 2N (integer coordinates)."""
+    n, ei, ej = _face(t)
+    return N * (n - ei - ej) + (2 * i + 1) * ei + (2 * j + 1) * ej
+
+
+def test_copy_corners_continues_rows_and_columns_around_the_cube_corner():
+    """FV3's copy_corners rule, checked against geometry instead of against itself: walking along a halo ROW
+    (direction 1) or COLUMN (direction 2) from the edge halo into the corner block, consecutive cells must be
+    neighbours on the cube (centres 2 apart on one face, sqrt 2 apart across an edge), i.e. the fill continues the
+    line around the corner into the face that really lies there."""
+    N, h = 8, 3
+    for t in range(6):
+        for ci, cj in ((-1, -1), (N, -1), (-1, N), (N, N)):  # first corner cell of SW, SE, NW, NE
+            si, sj = (-1 if ci < 0 else 1), (-1 if cj < 0 else 1)
+            for depth in range(h):
+                # direction 1: the row gj (in the south / north halo), walked in i from inside the tile into the corner
+                gj = cj + sj * depth
+                chain = [(ci - si, gj)] + [(ci + si * a, gj) for a in range(h)]
+                cells = [unfold(t, *chain[0], N)] + [unfold(t, *corner_fill_source(i, j, N, 1), N) for i, j in chain[1:]]
+                for a, b in zip(cells[:-1], cells[1:]):
+                    assert np.linalg.norm(_centre(*a, N) - _centre(*b, N)) <= 2.0 + 1e-9, (t, ci, cj, depth, "x")
+                # direction 2: the column gi (in the west / east halo), walked in j
+                gi = ci + si * depth
+                chain = [(gi, cj - sj)] + [(gi, cj + sj * a) for a in range(h)]
+                cells = [unfold(t, *chain[0], N)] + [unfold(t, *corner_fill_source(i, j, N, 2), N) for i, j in chain[1:]]
+                for a, b in zip(cells[:-1], cells[1:]):
+                    assert np.linalg.norm(_centre(*a, N) - _centre(*b, N)) <= 2.0 + 1e-9, (t, ci, cj, depth, "y")
+
+
+@pytest.mark.parametrize("layout", [(1, 1), (1, 2), (2, 2), (3, 2)])
+def test_corner_links_cover_every_halo_cell_once(layout):
+    N, h = 12, 3
+    part = CubedSpherePartitioner(N, layout, h, corners=True)
+    for r in range(part.total_ranks):
+        seen = np.zeros((part.nx + 2 * h, part.ny + 2 * h), dtype=int)
+        for l in part.links_into(r):
+            for d in range(l.nd):
+                for p in range(l.np_):
+                    seen[l.di0 + d * l.ddi + p * l.dpi + h, l.dj0 + d * l.ddj + p * l.dpj + h] += 1
+                    si, sj = l.si0 + d * l.sdi + p * l.spi, l.sj0 + d * l.sdj + p * l.spj
+                    assert 0 <= si < part.nx and 0 <= sj < part.ny  # corner fills read interiors too: one pass
+        want = np.ones_like(seen)
+        want[h:-h, h:-h] = 0
+        assert np.array_equal(seen, want)
+    flags = [part.cube_corner_flags(r) for r in range(part.total_ranks)]
+    assert sum(bin(f).count("1") for f in flags) == 24  # 6 tiles x 4 corners, whatever the layout
+
+
+@pytest.mark.parametrize("n_gpus", [1, 2, 4, 8])
+def test_global_id_exchange_with_corners(n_gpus):
+    """Corner blocks: the diagonal neighbour's ids inside a tile and across one tile edge, the copy_corners
+    (direction 1) ids at the cube corners -- through the same pack/segment/unpack tables."""
+    N, nk = 12, 2
+    part = CubedSpherePartitioner(N, layout_for(n_gpus), corners=True)
+    fields = [batch_field(part, n_gpus, g, nk) for g in range(n_gpus)]
+    exchange_in_process(part, n_gpus, fields, mover=cpu_mover)
+    for g in range(n_gpus):
+        check_field(part, n_gpus, g, fields[g], nk)
+        assert (fields[g] >= 0).all()  # no halo cell left unfilled
 
 
 @pytest.mark.parametrize("n_gpus", [1, 2, 4, 8])
