@@ -86,6 +86,49 @@ class FvTransport:
             call()
 
 
+class SplitTransport:
+    """One FV3-style transport step with the inner/outer operator splitting (S5b, ``fv_tp2d_split``):
+
+        halo update of q INCLUDING the corner blocks  ->  q_out = fv_tp2d_split(q, ...)
+
+    The partitioner must have been built with ``corners=True``: corner blocks then arrive from the diagonal
+    neighbour in the same exchange as the edge strips, and at the eight cube corners the exchange writes FV3's
+    copy_corners values for x-sweeps while the kernel derives the y-sweep values itself (``corner_flags``).
+    ``exchange`` = "nccl" (packed strips, grouped send/recv) or "p2p" (peer-memory pull; ``symmetric_q`` holds q).
+    """
+
+    def __init__(self, part: CubedSpherePartitioner, n_gpus: int, gpu: int, process_group=None, exchange: str = "nccl",
+                 symmetric_q=None):
+        if not part.corners:
+            raise ValueError("fv_tp2d_split reads the halo corners: build the partitioner with corners=True")
+        self.part, self.n_gpus, self.gpu = part, n_gpus, gpu
+        self.updater = HaloUpdater(part, n_gpus, gpu, process_group=process_group)
+        self.p2p = None
+        if exchange == "p2p":
+            from .p2p import P2PHaloUpdater
+
+            if symmetric_q is None:
+                raise ValueError('exchange="p2p" needs the SymmetricField that holds q')
+            self.p2p = P2PHaloUpdater(part, n_gpus, gpu, symmetric_q)
+        nsub = part.subdomains_per_gpu(n_gpus)
+        self.corner_flags_host = [part.cube_corner_flags(gpu * nsub + b) for b in range(nsub)]
+        self._flags = {}
+
+    def corner_flags(self, device) -> torch.Tensor:
+        if device not in self._flags:
+            self._flags[device] = torch.tensor(self.corner_flags_host, dtype=torch.int32, device=device)
+        return self._flags[device]
+
+    def step(self, q, crx, xfx, cry, yfx, area, rarea, q_out, fx_out=None, fy_out=None) -> None:
+        if self.p2p is not None:
+            if q.data_ptr() != self.p2p.sfield.field.data_ptr():
+                raise ValueError("p2p exchange: q is not the symmetric field this transport was built for")
+            self.p2p.update()
+        else:
+            self.updater.update(q)
+        stencils.fv_tp2d_split(q, crx, xfx, cry, yfx, area, rarea, q_out, fx_out, fy_out, corner_flags=self.corner_flags(q.device))
+
+
 class DycoreChain:
     """BASELINE config 5: horizontal FV transport followed by the vertical remap scan, per step
 
