@@ -34,6 +34,7 @@ SOURCES = {
     "k_fv_tma.cu": [],
     "tma_host.cu": [],
     "k_fv_split.cu": [],
+    "k_fv_split_stream.cu": [],
     "k_remap_slab.cu": ["-fmad=false"],
     "k_remap_ppm.cu": [],
     "k_halo.cu": [],

@@ -331,7 +331,14 @@ int launch_split(int ni, int nj, int nk, int nb, F3<const T> q, F3<const T> crx,
 
 }  // namespace
 
-// b2s_set_option("fv_split_ti", 0 | 56 | 120): maximum tile width (0 = 56);
+// streaming variant (k_fv_split_stream.cu)
+template <typename T>
+int fv_tp2d_split_stream(int ti, int ni, int nj, int nk, int nb, F3<const T> q, F3<const T> crx, F3<const T> xfx,
+                         F3<const T> cry, F3<const T> yfx, F2<const T> area, F2<const T> rarea, const int* corner_flags,
+                         F3<T> q_out, F3<T> fx_out, F3<T> fy_out, cudaStream_t s, bool* applicable);
+
+// b2s_set_option("fv_split_variant", 0 auto | 1 tile kernel | 2 streaming kernel);
+// b2s_set_option("fv_split_ti", 0 | 56 | 120): maximum tile / strip width (0 = 56);
 // TI + 6 and TI + 1 threads must fit a whole number of warps (64 and 128 threads)
 template <typename T>
 int fv_tp2d_split(int ni, int nj, int nk, int nb, F3<const T> q, F3<const T> crx, F3<const T> xfx, F3<const T> cry,
@@ -343,6 +350,12 @@ int fv_tp2d_split(int ni, int nj, int nk, int nb, F3<const T> q, F3<const T> crx
   if (ti != 56 && ti != 120) ti = 56;  // measured on C384x72: 1.77 ms (56 x 8 tiles) vs 1.92 ms (120 x 4)
   bool applicable = false;
   int rc;
+  const int variant = option("fv_split_variant", 0);
+  if (variant != 1) {
+    rc = fv_tp2d_split_stream<T>(ti, ni, nj, nk, nb, q, crx, xfx, cry, yfx, area, rarea, corner_flags, q_out, fx_out, fy_out, s,
+                                 &applicable);
+    if (applicable) return rc;
+  }
   if (ti == 120)
     rc = launch_split<T, 120, 4>(ni, nj, nk, nb, q, crx, xfx, cry, yfx, area, rarea, corner_flags, q_out, fx_out, fy_out, s, &applicable);
   else

@@ -318,7 +318,7 @@ def test_fv_tp2d_batched(st, corc, dtype):
 # ---- S5b fv_tp2d_split -------------------------------------------------------------------
 
 
-def _split_call(st, f, nk, dtype, fluxes=True, ti=0, batch=None):
+def _split_call(st, f, nk, dtype, fluxes=True, ti=0, batch=None, variant=0, jb=0):
     from b200stencil import _abi
 
     ni, nj = (f["rarea"][0] if batch else f["rarea"]).shape[-2:]
@@ -327,28 +327,36 @@ def _split_call(st, f, nk, dtype, fluxes=True, ti=0, batch=None):
     out = shp((ni, nj, nk))
     fx = shp((ni + 1, nj, nk)) if fluxes else None
     fy = shp((ni, nj + 1, nk)) if fluxes else None
-    _abi.set_option("fv_split_ti", ti)
+    for name, v in (("fv_split_ti", ti), ("fv_split_variant", variant), ("fv_split_jb", jb)):
+        _abi.set_option(name, v)
     try:
         st.fv_tp2d_split(d["q"], d["crx"], d["xfx"], d["cry"], d["yfx"], d["area"], d["rarea"], out, fx, fy)
     finally:
-        _abi.set_option("fv_split_ti", 0)
+        for name in ("fv_split_ti", "fv_split_variant", "fv_split_jb"):
+            _abi.set_option(name, 0)
     return out, fx, fy
 
 
 @pytest.mark.parametrize("shape", [(3, 3, 4), (12, 9, 3), (33, 17, 2), (130, 9, 2), (64, 20, 3), (257, 5, 1), (1, 1, 1)])
 @pytest.mark.parametrize("ti", [0, 56, 120])
+@pytest.mark.parametrize("variant,jb", [(1, 0), (2, 0), (2, 5)])
 @pytest.mark.parametrize("dtype", DTYPES)
-def test_fv_tp2d_split(st, corc, shape, ti, dtype):
+def test_fv_tp2d_split(st, corc, shape, ti, variant, jb, dtype):
+    """Tile kernel (variant 1) and streaming kernel (variant 2; jb = rows per CTA, 5 puts block boundaries inside
+    the small test domains) against the oracle; the two kernels use the same arithmetic -> identical bits."""
     ni, nj, nk = shape
     f = gen.fv_split_inputs(ni, nj, nk, dtype)
     ref, rfx, rfy = zeros_like_np(shape, dtype), zeros_like_np((ni + 1, nj, nk), dtype), zeros_like_np((ni, nj + 1, nk), dtype)
     corc.fv_tp2d_split(f["q"], f["crx"], f["xfx"], f["cry"], f["yfx"], f["area"], f["rarea"], ref, rfx, rfy)
-    out, fx, fy = _split_call(st, f, nk, dtype, True, ti)
+    out, fx, fy = _split_call(st, f, nk, dtype, True, ti, variant=variant, jb=jb)
     assert_close(down(out), ref, RTOL[dtype], "q_out")
     assert_close(down(fx), rfx, RTOL[dtype], "fx")
     assert_close(down(fy), rfy, RTOL[dtype], "fy")
-    out2, _, _ = _split_call(st, f, nk, dtype, False, ti)
+    out2, _, _ = _split_call(st, f, nk, dtype, False, ti, variant=variant, jb=jb)
     assert torch.equal(out, out2)  # the flux outputs are optional and do not change the update
+    if variant == 2:
+        tile, tfx, tfy = _split_call(st, f, nk, dtype, True, ti, variant=1)
+        assert torch.equal(out, tile) and torch.equal(fx, tfx) and torch.equal(fy, tfy)
 
 
 @pytest.mark.parametrize("shape", [(12, 9, 3), (70, 11, 2), (130, 20, 1)])
@@ -371,10 +379,20 @@ def test_fv_tp2d_split_cube_corners(st, corc, shape, dtype):
         refs.append(r)
     d = {k: up_batch([f[k] for f in fs]) for k in fs[0]}
     out = up_batch([np.zeros((ni, nj, nk), dtype)] * nb)
+    from b200stencil import _abi
+
     cf = torch.tensor(all_flags, dtype=torch.int32, device="cuda")
-    st.fv_tp2d_split(d["q"], d["crx"], d["xfx"], d["cry"], d["yfx"], d["area"], d["rarea"], out, corner_flags=cf)
-    for b in range(nb):
-        assert_close(down(out[b]), refs[b], RTOL[dtype], f"sub-domain {b} flags {all_flags[b]}")
+    for variant, jb in ((1, 0), (2, 0), (2, 7)):
+        _abi.set_option("fv_split_variant", variant)
+        _abi.set_option("fv_split_jb", jb)
+        try:
+            out.zero_()
+            st.fv_tp2d_split(d["q"], d["crx"], d["xfx"], d["cry"], d["yfx"], d["area"], d["rarea"], out, corner_flags=cf)
+        finally:
+            _abi.set_option("fv_split_variant", 0)
+            _abi.set_option("fv_split_jb", 0)
+        for b in range(nb):
+            assert_close(down(out[b]), refs[b], RTOL[dtype], f"variant {variant} sub-domain {b} flags {all_flags[b]}")
     plain = up_batch([np.zeros((ni, nj, nk), dtype)] * nb)
     st.fv_tp2d_split(d["q"], d["crx"], d["xfx"], d["cry"], d["yfx"], d["area"], d["rarea"], plain)
     assert not torch.equal(plain[0], out[0]) and torch.equal(plain[3], out[3])  # the flags matter, and only where set
