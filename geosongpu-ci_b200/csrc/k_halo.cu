@@ -15,18 +15,39 @@ namespace impl {
 
 static constexpr int kLinkWords = 10;
 
-// grid = (strip chunks, k, link): one thread per strip element, 32-bit index arithmetic only.
-// The faster-varying thread index follows whichever of (d, p) is contiguous on the SOURCE side,
-// so reads coalesce for north/south strips (p along i) and stay sector-dense for west/east ones
-// (d along i: 3 adjacent elements).
-template <typename T>
-__global__ void __launch_bounds__(256) k_halo_move(int nk, const int64_t* __restrict__ links, const T* src, T* dst) {
-  const int64_t* L = links + (int64_t)blockIdx.z * kLinkWords;
-  const int nd = (int)L[8], np = (int)L[9];
-  const int t = blockIdx.x * 256 + threadIdx.x;
-  if (t >= nd * np) return;
-  const int64_t ssd = L[1], ssp = L[2];
-  int d, p;
+// grid = (strip chunks, k chunks, link): one thread per strip element and KU levels.  The faster-varying
+// thread index follows whichever of (d, p) is contiguous on the SOURCE side, so reads coalesce for
+// north/south strips (p along i) and stay sector-dense for west/east ones (d along i: 3 adjacent elements).
+// KU = 1 is the default: measured on C384x72 (profiles/r01_halo_kernels.md) 11.9 us per update against 13.2
+// (KU = 4) and 14.2 (KU = 8), fp32 the same as fp64 -- the copy is bound by the number of 32-byte sectors the
+// west/east strips touch (3 elements per 3 KB row), not by bytes or by loads in flight.  With corner blocks
+// in the table (24 extra 3x3 links) KU = 4 wins (13.7 vs 16.0 us): b2s_set_option("halo_levels", 1 | 4 | 8).
+static constexpr int kKU = 1;
+
+template <typename T, int KU>
+__device__ __forceinline__ void copy_levels(const T* sp, int64_t ssk, T* dp, int64_t dsk, int nlev) {
+  T v[KU];
+  if (nlev >= KU) {
+#pragma unroll
+    for (int u = 0; u < KU; ++u) v[u] = sp[u * ssk];
+#pragma unroll
+    for (int u = 0; u < KU; ++u) dp[u * dsk] = v[u];
+  } else {
+#pragma unroll
+    for (int u = 0; u < KU; ++u)
+      if (u < nlev) v[u] = sp[u * ssk];
+#pragma unroll
+    for (int u = 0; u < KU; ++u)
+      if (u < nlev) dp[u * dsk] = v[u];
+  }
+}
+
+static int halo_levels() {
+  const int ku = option("halo_levels", kKU);
+  return ku == 4 || ku == 8 ? ku : kKU;
+}
+
+__device__ __forceinline__ void strip_decode(int t, int nd, int np, int64_t ssd, int& d, int& p) {
   if (ssd == 1 || ssd == -1) {  // depth runs along i on the source side
     d = t % nd;
     p = t / nd;
@@ -34,8 +55,19 @@ __global__ void __launch_bounds__(256) k_halo_move(int nk, const int64_t* __rest
     p = t % np;
     d = t / np;
   }
-  const int k = blockIdx.y;
-  dst[L[4] + d * L[5] + p * L[6] + k * L[7]] = src[L[0] + d * ssd + p * ssp + k * L[3]];
+}
+
+template <typename T, int KU>
+__global__ void __launch_bounds__(256) k_halo_move(int nk, const int64_t* __restrict__ links, const T* src, T* dst) {
+  const int64_t* L = links + (int64_t)blockIdx.z * kLinkWords;
+  const int nd = (int)L[8], np = (int)L[9];
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= nd * np) return;
+  const int64_t ssd = L[1], ssp = L[2], ssk = L[3], dsk = L[7];
+  int d, p;
+  strip_decode(t, nd, np, ssd, d, p);
+  const int k0 = blockIdx.y * KU;
+  copy_levels<T, KU>(src + (L[0] + d * ssd + p * ssp + k0 * ssk), ssk, dst + (L[4] + d * L[5] + p * L[6] + k0 * dsk), dsk, nk - k0);
 }
 
 template <typename T>
@@ -44,8 +76,11 @@ int halo_move(int nlinks, int nk, const int64_t* links, const T* src, T* dst, cu
   if (nlinks == 0) return B2S_OK;
   B2S_ARGCHECK(links && src && dst, "halo_move: null pointer");
   B2S_ARGCHECK(nk <= 65535 && nlinks <= 65535, "halo_move: grid too large (nk=%d, nlinks=%d)", nk, nlinks);
-  dim3 grid((max_strip + 255) / 256, nk, nlinks);
-  k_halo_move<T><<<grid, 256, 0, s>>>(nk, links, src, dst);
+  const int ku = halo_levels();
+  dim3 grid((max_strip + 255) / 256, (nk + ku - 1) / ku, nlinks);
+  if (ku == 8) k_halo_move<T, 8><<<grid, 256, 0, s>>>(nk, links, src, dst);
+  else if (ku == 4) k_halo_move<T, 4><<<grid, 256, 0, s>>>(nk, links, src, dst);
+  else k_halo_move<T, 1><<<grid, 256, 0, s>>>(nk, links, src, dst);
   return check_launch("halo_move");
 }
 
@@ -66,24 +101,18 @@ int halo_move(int nlinks, int nk, int max_strip, const int64_t* links, const T* 
 // -------------------------------------------------------------------------------------------
 static constexpr int kPullWords = 11;
 
-template <typename T>
+template <typename T, int KU>
 __global__ void __launch_bounds__(256) k_halo_pull(int nk, const int64_t* __restrict__ links, T* dst) {
   const int64_t* L = links + (int64_t)blockIdx.z * kPullWords;
   const int nd = (int)L[8], np = (int)L[9];
   const int t = blockIdx.x * 256 + threadIdx.x;
   if (t >= nd * np) return;
   const T* src = reinterpret_cast<const T*>(static_cast<uintptr_t>(L[10]));
-  const int64_t ssd = L[1], ssp = L[2];
+  const int64_t ssd = L[1], ssp = L[2], ssk = L[3], dsk = L[7];
   int d, p;
-  if (ssd == 1 || ssd == -1) {
-    d = t % nd;
-    p = t / nd;
-  } else {
-    p = t % np;
-    d = t / np;
-  }
-  const int k = blockIdx.y;
-  dst[L[4] + d * L[5] + p * L[6] + k * L[7]] = src[L[0] + d * ssd + p * ssp + k * L[3]];
+  strip_decode(t, nd, np, ssd, d, p);
+  const int k0 = blockIdx.y * KU;
+  copy_levels<T, KU>(src + (L[0] + d * ssd + p * ssp + k0 * ssk), ssk, dst + (L[4] + d * L[5] + p * L[6] + k0 * dsk), dsk, nk - k0);
 }
 
 template <typename T>
@@ -92,8 +121,11 @@ int halo_pull(int nlinks, int nk, int max_strip, const int64_t* links, T* dst, c
   if (nlinks == 0) return B2S_OK;
   B2S_ARGCHECK(links && dst, "halo_pull: null pointer");
   B2S_ARGCHECK(nk <= 65535 && nlinks <= 65535, "halo_pull: grid too large (nk=%d, nlinks=%d)", nk, nlinks);
-  dim3 grid((max_strip + 255) / 256, nk, nlinks);
-  k_halo_pull<T><<<grid, 256, 0, s>>>(nk, links, dst);
+  const int ku = halo_levels();
+  dim3 grid((max_strip + 255) / 256, (nk + ku - 1) / ku, nlinks);
+  if (ku == 8) k_halo_pull<T, 8><<<grid, 256, 0, s>>>(nk, links, dst);
+  else if (ku == 4) k_halo_pull<T, 4><<<grid, 256, 0, s>>>(nk, links, dst);
+  else k_halo_pull<T, 1><<<grid, 256, 0, s>>>(nk, links, dst);
   return check_launch("halo_pull");
 }
 

@@ -31,7 +31,8 @@ static std::map<std::string, int> g_options = {
     {"remap_ppm_cols", 0},  // remap_ppm: columns per CTA, 0 auto, 16 | 32 (k_remap_ppm.cu)
     {"remap_ppm_loader", 0},// remap_ppm: 0 auto, 1 cp.async, 2 TMA
     {"fv_split_variant", 0},// fv_tp2d_split: 0 auto, 1 tile kernel, 2 streaming kernel (k_fv_split_stream.cu)
-    {"fv_split_jb", 0},     // streaming kernel: rows per CTA, 0 auto (64)
+    {"fv_split_jb", 0},     // streaming kernel: rows per CTA, 0 auto (128)
+    {"halo_levels", 0},     // halo_move / halo_pull: levels per thread, 0 auto (1), 1 | 4 | 8 (k_halo.cu)
     {"fv_split_ti", 0},     // fv_tp2d_split tile width: 0 auto, 64 | 128 (k_fv_split.cu)
     {"sat_unroll", 0},      // levels per load batch of k_saturation_adjust: 0 auto, 1 | 2 | 4
     {"sat_kchunk", 0},      // levels per thread of k_saturation_adjust: 0 auto (8)
