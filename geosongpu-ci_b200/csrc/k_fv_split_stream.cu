@@ -54,7 +54,7 @@ struct StreamTile {
   static constexpr int YF_OFF = CY_OFF + round_up_(RB * WQ * (int)sizeof(T), 128);
   static constexpr int STAGE_BYTES = YF_OFF + round_up_(RB * WQ * (int)sizeof(T), 128);
   static constexpr int TX_BYTES = RB * (4 * WQ + 2 * WX) * (int)sizeof(T);
-  static constexpr int P = TI + 8;                                      // pitch of the exchange rows
+  static constexpr int P = TI + 16;                                     // pitch of the exchange rows (idle lanes read up to column THREADS + 5)
   static constexpr int XROWS_OFF = 2 * STAGE_BYTES;                     // fx2[2][P], q_i[2][P], fxa[2][P]
   static constexpr int BAR_OFF = round_up_(XROWS_OFF + 6 * P * (int)sizeof(T), 16);
   static constexpr int SMEM_BYTES = BAR_OFF + 16;
@@ -72,7 +72,7 @@ struct StreamParams {
   F3<T> qout, fxo, fyo;
 };
 
-template <typename T, int TI>
+template <typename T, int TI, bool FLUX_OUT>
 __global__ void __launch_bounds__(StreamTile<T, TI>::THREADS) k_fv_split_stream(
     const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_ar,
     const __grid_constant__ CUtensorMap tm_cx, const __grid_constant__ CUtensorMap tm_xf,
@@ -123,17 +123,31 @@ __global__ void __launch_bounds__(StreamTile<T, TI>::THREADS) k_fv_split_stream(
   }
   __syncthreads();
 
-  // roles of this thread
-  const int c = tid;                   // tile column (compute column i0 - 3 + c)
-  const bool ycol = c < tw + 6;        // takes part in the y-direction phases
-  const bool xint = c <= tw;           // x-interface i0 + c
+  // Roles of this thread.  EVERY thread runs EVERY phase of every row, whatever its role: lanes without a role
+  // in a phase compute on whatever sits in shared memory at their (in-bounds) index and their results are never
+  // read or stored.  The first version guarded each phase with `if (role)`: the merges cost 47 register moves, 30
+  // branch / reconvergence instructions and 9 zero-fills per warp-row, a quarter of all issued instructions
+  // (profiles/r01_next_rows.md).  Only global stores and loads carry predicates.
+  const int c = tid;                   // tile column (compute column i0 - 3 + c), x-interface i0 + c
   const int cc = c - 3;                // compute column of the tile, valid for 3 <= c < tw + 3
+  const int ccr = max(cc, 0);          // shared-row index of the compute-column phases (idle lanes read column 0)
   const bool ccol = c >= 3 && c < tw + 3;
   const int ig = i0 + cc;              // global compute column
   const bool store_col = ccol && ig < P.ni;
+  const bool fx_col = FLUX_OUT && c <= tw && i0 + c <= P.ni && P.fxo.p != nullptr;
+  const bool fy_col = FLUX_OUT && store_col && P.fyo.p != nullptr;
   const int flags = P.corner_flags ? __ldg(P.corner_flags + b) : 0;
   const int ia = i0 - 3 + c;
-  const bool patch = flags != 0 && ycol && (ia < 0 || (ia >= P.ni && ia < P.ni + 3));
+  const bool patch = flags != 0 && c < tw + 6 && (ia < 0 || (ia >= P.ni && ia < P.ni + 3));
+  const int nrows = jc1 - jc0;
+
+  // running pointers of the rows touched at iteration n (advanced once per row, dereferenced under the row guards):
+  // q_out and fx_out row r - 3 = jc0 - 6 + n, fy_out and rarea row r - 2 = jc0 - 5 + n
+  T* qo_p = P.qout.at(ig, jc0 - 6, k, b);
+  const T* ra_p = P.rarea.at(ig, jc0 - 5, b);
+  T* fx_p = FLUX_OUT ? P.fxo.at(i0 + c, jc0 - 6, k, b) : nullptr;
+  T* fy_p = FLUX_OUT ? P.fyo.at(ig, jc0 - 5, k, b) : nullptr;
+  const int64_t qo_sj = P.qout.sj, ra_sj = P.rarea.sj, fx_sj = P.fxo.sj, fy_sj = P.fyo.sj;
 
   // register state
   T qw0 = T(0), qw1 = T(0), qw2 = T(0), qw3 = T(0), qw4 = T(0), qw5 = T(0);  // q rows r-5 .. r (y-sweep view)
@@ -146,108 +160,98 @@ __global__ void __launch_bounds__(StreamTile<T, TI>::THREADS) k_fv_split_stream(
   for (int u = 0; u < RB; ++u) cx_ring[u] = xf_ring[u] = fx2_ring[u] = ar_ring[u] = T(0);
   T ra_next = T(0);  // rarea of the row that will be stored next iteration
 
+  static_assert(RB % 2 == 0, "the exchange rows are indexed by the parity of the chunk row");
   for (int m = 0; m < nchunk; ++m) {
     mbar_wait(&full[m & 1], (m >> 1) & 1);
     const unsigned char* st = smem + (m & 1) * G::STAGE_BYTES;
-    const T* Qs = reinterpret_cast<const T*>(st + G::Q_OFF) + P.s_q;    // [RB][WQ] (row, column i0-3+c)
-    const T* ARs = reinterpret_cast<const T*>(st + G::AR_OFF) + P.s_ar;
-    const T* CXs = reinterpret_cast<const T*>(st + G::CX_OFF) + P.s_cx;  // [RB][WX] (row, interface i0+c)
+    const T* Qs = reinterpret_cast<const T*>(st + G::Q_OFF) + P.s_q + c;     // [RB][WQ] (row, column i0-3+c)
+    const T* ARs = reinterpret_cast<const T*>(st + G::AR_OFF) + P.s_ar + c;
+    const T* CXs = reinterpret_cast<const T*>(st + G::CX_OFF) + P.s_cx + c;  // [RB][WX] (row, interface i0+c)
     const T* XFs = reinterpret_cast<const T*>(st + G::XF_OFF) + P.s_xf;
-    const T* CYs = reinterpret_cast<const T*>(st + G::CY_OFF) + P.s_cy;  // [RB][WQ] (interface r-2, column i0-3+c)
-    const T* YFs = reinterpret_cast<const T*>(st + G::YF_OFF) + P.s_yf;
+    const T* CYs = reinterpret_cast<const T*>(st + G::CY_OFF) + P.s_cy + c;  // [RB][WQ] (interface r-2, column i0-3+c)
+    const T* YFs = reinterpret_cast<const T*>(st + G::YF_OFF) + P.s_yf + c;
+    // rows past the last one of the block (the chunk is always run in full) read TMA zero-fill or the next block's
+    // rows; nothing of them is stored
 #pragma unroll
     for (int rr = 0; rr < RB; ++rr) {
       const int n = m * RB + rr;  // iteration; uniform over the CTA
-      if (n < niter) {
-        const int r = r0 + n;
-        const int par = n & 1;
-        constexpr int kNow = 0;  // ring slot helpers below use rr directly
-        (void)kNow;
-        // ---- 1. inner x-sweep of row r, thread = interface ----
-        T fx2 = T(0), cx = T(0), xf = T(0);
-        if (xint) {
-          const T* row = Qs + rr * WQ + c;
-          const T x0 = row[0], x1 = row[1], x2 = row[2], x3 = row[3], x4 = row[4], x5 = row[5];
-          cx = CXs[rr * WX + c];
-          xf = XFs[rr * WX + c];
-          fx2 = ppm_flux_from_al(x2, x3, ppm_al(x0, x1, x2, x3), ppm_al(x1, x2, x3, x4), ppm_al(x2, x3, x4, x5), cx);
-          fx2row[par * PP + c] = fx2;
+      const int r = r0 + n;
+      const int par = rr & 1;     // == n & 1
+      // ---- 1. inner x-sweep of row r, thread = interface ----
+      const T* row = Qs + rr * WQ;
+      const T x0 = row[0], x1 = row[1], x2 = row[2], x3 = row[3], x4 = row[4], x5 = row[5];
+      const T cx = CXs[rr * WX];
+      const T xf = XFs[rr * WX + c];
+      const T fx2 = ppm_flux_from_al(x2, x3, ppm_al(x0, x1, x2, x3), ppm_al(x1, x2, x3, x4), ppm_al(x2, x3, x4, x5), cx);
+      fx2row[par * PP + c] = fx2;
+      // ---- 2. inner y-sweep: interface r-2, then q_i of row r-3; thread = tile column ----
+      const T q_new = x0;
+      const T ar_new = ARs[rr * WQ];
+      T qy = q_new;
+      if (patch && (r < 0 || r >= P.nj) && r < P.nj + 3) {  // copy_corners direction 2 (see k_fv_split.cu)
+        const int bit = ia < 0 ? (r < 0 ? 1 : 4) : (r < 0 ? 2 : 8);
+        if (flags & bit) {
+          int si, sj;
+          if (bit == 1) si = -r - 1, sj = ia;
+          else if (bit == 2) si = P.ni + r, sj = P.ni - 1 - ia;
+          else if (bit == 8) si = P.ni + P.nj - 1 - r, sj = ia - P.ni + P.nj;
+          else si = r - P.nj, sj = P.nj - 1 - ia;
+          qy = __ldg(P.q.at(si, sj, k, b));
         }
-        // ---- 2. inner y-sweep: interface r-2, then q_i of row r-3; thread = tile column ----
-        T fy2 = T(0), yf = T(0), cy = T(0), q_new = T(0), ar_new = T(0);
-        if (ycol) {
-          q_new = Qs[rr * WQ + c];
-          ar_new = ARs[rr * WQ + c];
-          T qy = q_new;
-          if (patch && (r < 0 || r >= P.nj) && r < P.nj + 3) {  // copy_corners direction 2 (see k_fv_split.cu)
-            const int bit = ia < 0 ? (r < 0 ? 1 : 4) : (r < 0 ? 2 : 8);
-            if (flags & bit) {
-              int si, sj;
-              if (bit == 1) si = -r - 1, sj = ia;
-              else if (bit == 2) si = P.ni + r, sj = P.ni - 1 - ia;
-              else if (bit == 8) si = P.ni + P.nj - 1 - r, sj = ia - P.ni + P.nj;
-              else si = r - P.nj, sj = P.nj - 1 - ia;
-              qy = __ldg(P.q.at(si, sj, k, b));
-            }
-          }
-          qw0 = qw1, qw1 = qw2, qw2 = qw3, qw3 = qw4, qw4 = qw5, qw5 = qy;
-          const T al_c = ppm_al(qw2, qw3, qw4, qw5);
-          cy = CYs[rr * WQ + c];
-          yf = YFs[rr * WQ + c];
-          fy2 = ppm_flux_from_al(qw2, qw3, qal_a, qal_b, al_c, cy);  // interface r-2: between rows r-3 (qw2) and r-2 (qw3)
-          qal_a = qal_b, qal_b = al_c;
-          const T fyy = mul_rn(yf, fy2);
-          // q_i of row r-3: interfaces r-3 (previous iteration) and r-2; q of row r-3 as stored, its area from the ring
-          const T arj = ar_ring[(rr + 1) % RB];
-          const T ra = add_rn(arj, sub_rn(yf_prev, yf));
-          qirow[par * PP + c] = mul_rn(fma_rn(q_m3, arj, sub_rn(fyy_prev, fyy)), rcp_fast_(ra));
-          fyy_prev = fyy, yf_prev = yf;
-        }
-        __syncthreads();
-        // ---- 3. q_j of row r, outer y-sweep at interface r-2; thread = compute column ----
-        T fya = T(0);
-        if (ccol) {
-          const T xl = XFs[rr * WX + cc], xh = XFs[rr * WX + cc + 1];
-          const T ra = add_rn(ar_new, sub_rn(xl, xh));
-          const T num = fma_rn(q_new, ar_new, sub_rn(mul_rn(xl, fx2row[par * PP + cc]), mul_rn(xh, fx2row[par * PP + cc + 1])));
-          const T qj = mul_rn(num, rcp_fast_(ra));
-          jw0 = jw1, jw1 = jw2, jw2 = jw3, jw3 = jw4, jw4 = jw5, jw5 = qj;
-          const T al_c = ppm_al(jw2, jw3, jw4, jw5);
-          const T fo = ppm_flux_from_al(jw2, jw3, jal_a, jal_b, al_c, cy);
-          jal_a = jal_b, jal_b = al_c;
-          fya = mul_rn(mul_rn(T(0.5), add_rn(fo, fy2)), yf);  // averaged y-flux at interface r-2
-          const int jf = r - 2;
-          if (n >= 5 && jf >= jc0 && jf <= jc1 && store_col && P.fyo.p) __stcs(P.fyo.at(ig, jf, k, b), fya);
-        }
-        // ---- 4. outer x-sweep of row r-3 on q_i; thread = interface ----
-        if (xint) {
-          const T* row = qirow + par * PP + c;
-          const T x0 = row[0], x1 = row[1], x2 = row[2], x3 = row[3], x4 = row[4], x5 = row[5];
-          const T cxj = cx_ring[(rr + 1) % RB], xfj = xf_ring[(rr + 1) % RB], f2j = fx2_ring[(rr + 1) % RB];
-          const T fo = ppm_flux_from_al(x2, x3, ppm_al(x0, x1, x2, x3), ppm_al(x1, x2, x3, x4), ppm_al(x2, x3, x4, x5), cxj);
-          const T fxa = mul_rn(mul_rn(T(0.5), add_rn(fo, f2j)), xfj);
-          fxarow[par * PP + c] = fxa;
-          const int j = r - 3;
-          if (n >= 6 && j < jc1 && P.fxo.p && i0 + c <= P.ni) __stcs(P.fxo.at(i0 + c, j, k, b), fxa);
-        }
-        // rings: this row's values replace row r-4's
-        cx_ring[rr] = cx, xf_ring[rr] = xf, fx2_ring[rr] = fx2, ar_ring[rr] = ar_new;
-        __syncthreads();
-        // ---- 5. update of row r-3; thread = compute column ----
-        {
-          const int j = r - 3;
-          if (ccol) {
-            if (n >= 6 && j < jc1 && store_col) {
-              const T fxl = fxarow[par * PP + cc], fxh = fxarow[par * PP + cc + 1];
-              __stcs(P.qout.at(ig, j, k, b), fma_rn(ra_next, add_rn(sub_rn(fxl, fxh), sub_rn(fya_prev, fya)), q_m3));
-            }
-            fya_prev = fya;
-            // rarea of the row stored next iteration (r - 2), in flight across one iteration
-            const int jn = j + 1;
-            if (store_col && jn >= jc0 && jn < jc1) ra_next = __ldg(P.rarea.at(ig, jn, b));
-          }
-          q_m3 = q_m2, q_m2 = q_m1, q_m1 = q_new;
-        }
+      }
+      qw0 = qw1, qw1 = qw2, qw2 = qw3, qw3 = qw4, qw4 = qw5, qw5 = qy;
+      const T qal_c = ppm_al(qw2, qw3, qw4, qw5);
+      const T cy = CYs[rr * WQ];
+      const T yf = YFs[rr * WQ];
+      const T fy2 = ppm_flux_from_al(qw2, qw3, qal_a, qal_b, qal_c, cy);  // interface r-2: between rows r-3 (qw2) and r-2 (qw3)
+      qal_a = qal_b, qal_b = qal_c;
+      const T fyy = mul_rn(yf, fy2);
+      {
+        // q_i of row r-3: interfaces r-3 (previous iteration) and r-2; q of row r-3 as stored, its area from the ring
+        const T arj = ar_ring[(rr + 1) % RB];
+        const T ra = add_rn(arj, sub_rn(yf_prev, yf));
+        qirow[par * PP + c] = mul_rn(fma_rn(q_m3, arj, sub_rn(fyy_prev, fyy)), rcp_fast_(ra));
+        fyy_prev = fyy, yf_prev = yf;
+      }
+      __syncthreads();
+      // ---- 3. q_j of row r, outer y-sweep at interface r-2; thread = compute column ----
+      T fya;
+      {
+        const T xl = XFs[rr * WX + ccr], xh = XFs[rr * WX + ccr + 1];
+        const T ra = add_rn(ar_new, sub_rn(xl, xh));
+        const T num = fma_rn(q_new, ar_new, sub_rn(mul_rn(xl, fx2row[par * PP + ccr]), mul_rn(xh, fx2row[par * PP + ccr + 1])));
+        const T qj = mul_rn(num, rcp_fast_(ra));
+        jw0 = jw1, jw1 = jw2, jw2 = jw3, jw3 = jw4, jw4 = jw5, jw5 = qj;
+        const T jal_c = ppm_al(jw2, jw3, jw4, jw5);
+        const T fo = ppm_flux_from_al(jw2, jw3, jal_a, jal_b, jal_c, cy);
+        jal_a = jal_b, jal_b = jal_c;
+        fya = mul_rn(mul_rn(T(0.5), add_rn(fo, fy2)), yf);  // averaged y-flux at interface r-2
+        if (FLUX_OUT && fy_col && n >= 5 && n <= 5 + nrows) __stcs(fy_p, fya);  // interfaces jc0 .. jc1
+      }
+      // ---- 4. outer x-sweep of row r-3 on q_i; thread = interface ----
+      {
+        const T* qi = qirow + par * PP + c;
+        const T y0 = qi[0], y1 = qi[1], y2 = qi[2], y3 = qi[3], y4 = qi[4], y5 = qi[5];
+        const T cxj = cx_ring[(rr + 1) % RB], xfj = xf_ring[(rr + 1) % RB], f2j = fx2_ring[(rr + 1) % RB];
+        const T fo = ppm_flux_from_al(y2, y3, ppm_al(y0, y1, y2, y3), ppm_al(y1, y2, y3, y4), ppm_al(y2, y3, y4, y5), cxj);
+        const T fxa = mul_rn(mul_rn(T(0.5), add_rn(fo, f2j)), xfj);
+        fxarow[par * PP + c] = fxa;
+        if (FLUX_OUT && fx_col && (unsigned)(n - 6) < (unsigned)nrows) __stcs(fx_p, fxa);
+      }
+      // rings: this row's values replace row r-4's
+      cx_ring[rr] = cx, xf_ring[rr] = xf, fx2_ring[rr] = fx2, ar_ring[rr] = ar_new;
+      __syncthreads();
+      // ---- 5. update of row r-3; thread = compute column ----
+      {
+        const T fxl = fxarow[par * PP + ccr], fxh = fxarow[par * PP + ccr + 1];
+        if (store_col && (unsigned)(n - 6) < (unsigned)nrows)
+          __stcs(qo_p, fma_rn(ra_next, add_rn(sub_rn(fxl, fxh), sub_rn(fya_prev, fya)), q_m3));
+        fya_prev = fya;
+        // rarea of the row stored next iteration (r - 2), in flight across one iteration
+        if (store_col && (unsigned)(n - 5) < (unsigned)nrows) ra_next = __ldg(ra_p);
+        q_m3 = q_m2, q_m2 = q_m1, q_m1 = q_new;
+        qo_p += qo_sj, ra_p += ra_sj;
+        if (FLUX_OUT) fx_p += fx_sj, fy_p += fy_sj;
       }
     }
     // every read of this stage is behind the last barrier of its last row: refill it with chunk m + 2
@@ -278,13 +282,14 @@ int launch_stream(int ni, int nj, int nk, int nb, F3<const T> q, F3<const T> crx
       make_map<T>(&mcy, fcy.base, cry.sj, cry.sk, cry.sb, ni + 6 + fcy.off, nj + 1, nk, nb, G::WQ, RB) &&
       make_map<T>(&myx, fyx.base, yfx.sj, yfx.sk, yfx.sb, ni + 6 + fyx.off, nj + 1, nk, nb, G::WQ, RB);
   if (!ok) return B2S_OK;
-  auto kern = k_fv_split_stream<T, TI>;
-  static bool configured = false;
-  if (!configured) {
+  const bool flux_out = fxo.p != nullptr || fyo.p != nullptr;
+  auto kern = flux_out ? k_fv_split_stream<T, TI, true> : k_fv_split_stream<T, TI, false>;
+  static bool configured[2] = {false, false};
+  if (!configured[flux_out]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (e != cudaSuccess) return set_error((int)e, "fv_tp2d_split(stream): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    configured = true;
+    configured[flux_out] = true;
   }
   StreamParams<T> P;
   P.ni = ni, P.nj = nj, P.nk = nk;
