@@ -37,7 +37,7 @@ __device__ __forceinline__ double rcp_fast_(double x) {
   e = __fma_rn(-x, r, 1.0);
   return __fma_rn(r, e, r);
 }
-__device__ __forceinline__ float rcp_fast_(float x) { return __frcp_rn(x); }
+__device__ __forceinline__ float rcp_fast_(float x) { return __frcp_rn(x); }  // kept IEEE: the tile kernel must match bit for bit
 
 constexpr int RB = 4;  // rows per chunk = depth of the register rings
 
@@ -72,8 +72,8 @@ struct StreamParams {
   F3<T> qout, fxo, fyo;
 };
 
-template <typename T, int TI, bool FLUX_OUT>
-__global__ void __launch_bounds__(StreamTile<T, TI>::THREADS) k_fv_split_stream(
+template <typename T, int TI, bool FLUX_OUT, int RP>
+__global__ void __launch_bounds__(StreamTile<T, TI>::THREADS, (sizeof(T) == 8 ? 512 : 704) / StreamTile<T, TI>::THREADS) k_fv_split_stream(
     const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_ar,
     const __grid_constant__ CUtensorMap tm_cx, const __grid_constant__ CUtensorMap tm_xf,
     const __grid_constant__ CUtensorMap tm_cy, const __grid_constant__ CUtensorMap tm_yf, const StreamParams<T> P) {
@@ -142,25 +142,28 @@ __global__ void __launch_bounds__(StreamTile<T, TI>::THREADS) k_fv_split_stream(
   const int nrows = jc1 - jc0;
 
   // running pointers of the rows touched at iteration n (advanced once per row, dereferenced under the row guards):
-  // q_out and fx_out row r - 3 = jc0 - 6 + n, fy_out and rarea row r - 2 = jc0 - 5 + n
+  // q_out and fx_out row r - 3 = jc0 - 6 + n, fy_out row r - 2 = jc0 - 5 + n
   T* qo_p = P.qout.at(ig, jc0 - 6, k, b);
-  const T* ra_p = P.rarea.at(ig, jc0 - 5, b);
+  const T* ra_p = P.rarea.at(ig, jc0 - 6 + RP, b);  // row stored at iteration n + RP
   T* fx_p = FLUX_OUT ? P.fxo.at(i0 + c, jc0 - 6, k, b) : nullptr;
   T* fy_p = FLUX_OUT ? P.fyo.at(ig, jc0 - 5, k, b) : nullptr;
   const int64_t qo_sj = P.qout.sj, ra_sj = P.rarea.sj, fx_sj = P.fxo.sj, fy_sj = P.fyo.sj;
 
   // register state
-  T qw0 = T(0), qw1 = T(0), qw2 = T(0), qw3 = T(0), qw4 = T(0), qw5 = T(0);  // q rows r-5 .. r (y-sweep view)
-  T jw0 = T(0), jw1 = T(0), jw2 = T(0), jw3 = T(0), jw4 = T(0), jw5 = T(0);  // q_j rows r-5 .. r
+  T qw2 = T(0), qw3 = T(0), qw4 = T(0), qw5 = T(0);  // q rows r-3 .. r (y-sweep view)
+  T jw2 = T(0), jw3 = T(0), jw4 = T(0), jw5 = T(0);  // q_j rows r-3 .. r
   T qal_a = T(0), qal_b = T(0), jal_a = T(0), jal_b = T(0);                  // carried interface values of the two windows
   T q_m3 = T(0), q_m2 = T(0), q_m1 = T(0);                                   // q rows r-3 .. r-1 as stored (direction-1 corners)
   T fyy_prev = T(0), yf_prev = T(0), fya_prev = T(0);                        // interface r-3: yfx*fy2, yfx, averaged flux
   T cx_ring[RB], xf_ring[RB], fx2_ring[RB], ar_ring[RB];                     // rows r-3 .. r of this thread's interface / column
 #pragma unroll
   for (int u = 0; u < RB; ++u) cx_ring[u] = xf_ring[u] = fx2_ring[u] = ar_ring[u] = T(0);
-  T ra_next = T(0);  // rarea of the row that will be stored next iteration
+  T q_st[RP], cxj[RP], xfj[RP], f2j[RP];  // per row of a group: q of row r-3 as stored, interface values of row r-3
 
-  static_assert(RB % 2 == 0, "the exchange rows are indexed by the parity of the chunk row");
+  static_assert(RB % 2 == 0 && RB % RP == 0 && (RP == 1 || RP == 2), "exchange rows are indexed by the parity of the chunk row");
+  T ra_row[RP];  // rarea of the rows stored by the NEXT group (in flight across one group)
+#pragma unroll
+  for (int h = 0; h < RP; ++h) ra_row[h] = T(0);
   for (int m = 0; m < nchunk; ++m) {
     mbar_wait(&full[m & 1], (m >> 1) & 1);
     const unsigned char* st = smem + (m & 1) * G::STAGE_BYTES;
@@ -171,87 +174,108 @@ __global__ void __launch_bounds__(StreamTile<T, TI>::THREADS) k_fv_split_stream(
     const T* CYs = reinterpret_cast<const T*>(st + G::CY_OFF) + P.s_cy + c;  // [RB][WQ] (interface r-2, column i0-3+c)
     const T* YFs = reinterpret_cast<const T*>(st + G::YF_OFF) + P.s_yf + c;
     // rows past the last one of the block (the chunk is always run in full) read TMA zero-fill or the next block's
-    // rows; nothing of them is stored
+    // rows; nothing of them is stored.
+    // A group = RP consecutive rows taken through the five phases together (two barriers per group): with RP = 2
+    // the two rows' flux chains are independent, which doubles the instruction-level parallelism between barriers.
 #pragma unroll
-    for (int rr = 0; rr < RB; ++rr) {
-      const int n = m * RB + rr;  // iteration; uniform over the CTA
-      const int r = r0 + n;
-      const int par = rr & 1;     // == n & 1
-      // ---- 1. inner x-sweep of row r, thread = interface ----
-      const T* row = Qs + rr * WQ;
-      const T x0 = row[0], x1 = row[1], x2 = row[2], x3 = row[3], x4 = row[4], x5 = row[5];
-      const T cx = CXs[rr * WX];
-      const T xf = XFs[rr * WX + c];
-      const T fx2 = ppm_flux_from_al(x2, x3, ppm_al(x0, x1, x2, x3), ppm_al(x1, x2, x3, x4), ppm_al(x2, x3, x4, x5), cx);
-      fx2row[par * PP + c] = fx2;
-      // ---- 2. inner y-sweep: interface r-2, then q_i of row r-3; thread = tile column ----
-      const T q_new = x0;
-      const T ar_new = ARs[rr * WQ];
-      T qy = q_new;
-      if (patch && (r < 0 || r >= P.nj) && r < P.nj + 3) {  // copy_corners direction 2 (see k_fv_split.cu)
-        const int bit = ia < 0 ? (r < 0 ? 1 : 4) : (r < 0 ? 2 : 8);
-        if (flags & bit) {
-          int si, sj;
-          if (bit == 1) si = -r - 1, sj = ia;
-          else if (bit == 2) si = P.ni + r, sj = P.ni - 1 - ia;
-          else if (bit == 8) si = P.ni + P.nj - 1 - r, sj = ia - P.ni + P.nj;
-          else si = r - P.nj, sj = P.nj - 1 - ia;
-          qy = __ldg(P.q.at(si, sj, k, b));
+    for (int g = 0; g < RB / RP; ++g) {
+      T q_new[RP], ar_new[RP], cy[RP], yf[RP], fy2[RP], fya[RP];
+      // ---- phases 1 + 2 ----
+#pragma unroll
+      for (int h = 0; h < RP; ++h) {
+        const int rr = g * RP + h;
+        const int r = r0 + m * RB + rr;
+        const int par = rr & 1;  // == iteration parity
+        // 1. inner x-sweep of row r, thread = interface
+        const T* row = Qs + rr * WQ;
+        const T x0 = row[0], x1 = row[1], x2 = row[2], x3 = row[3], x4 = row[4], x5 = row[5];
+        const T cx = CXs[rr * WX];
+        const T xf = XFs[rr * WX + c];
+        const T fx2 = ppm_flux_from_al(x2, x3, ppm_al(x0, x1, x2, x3), ppm_al(x1, x2, x3, x4), ppm_al(x2, x3, x4, x5), cx);
+        fx2row[par * PP + c] = fx2;
+        // 2. inner y-sweep: interface r-2, then q_i of row r-3; thread = tile column
+        q_new[h] = x0;
+        ar_new[h] = ARs[rr * WQ];
+        T qy = x0;
+        if (patch && (r < 0 || r >= P.nj) && r < P.nj + 3) {  // copy_corners direction 2 (see k_fv_split.cu)
+          const int bit = ia < 0 ? (r < 0 ? 1 : 4) : (r < 0 ? 2 : 8);
+          if (flags & bit) {
+            int si, sj;
+            if (bit == 1) si = -r - 1, sj = ia;
+            else if (bit == 2) si = P.ni + r, sj = P.ni - 1 - ia;
+            else if (bit == 8) si = P.ni + P.nj - 1 - r, sj = ia - P.ni + P.nj;
+            else si = r - P.nj, sj = P.nj - 1 - ia;
+            qy = __ldg(P.q.at(si, sj, k, b));
+          }
         }
-      }
-      qw0 = qw1, qw1 = qw2, qw2 = qw3, qw3 = qw4, qw4 = qw5, qw5 = qy;
-      const T qal_c = ppm_al(qw2, qw3, qw4, qw5);
-      const T cy = CYs[rr * WQ];
-      const T yf = YFs[rr * WQ];
-      const T fy2 = ppm_flux_from_al(qw2, qw3, qal_a, qal_b, qal_c, cy);  // interface r-2: between rows r-3 (qw2) and r-2 (qw3)
-      qal_a = qal_b, qal_b = qal_c;
-      const T fyy = mul_rn(yf, fy2);
-      {
-        // q_i of row r-3: interfaces r-3 (previous iteration) and r-2; q of row r-3 as stored, its area from the ring
+        qw2 = qw3, qw3 = qw4, qw4 = qw5, qw5 = qy;  // q rows r-3 .. r (y-sweep view)
+        const T qal_c = ppm_al(qw2, qw3, qw4, qw5);
+        cy[h] = CYs[rr * WQ];
+        yf[h] = YFs[rr * WQ];
+        fy2[h] = ppm_flux_from_al(qw2, qw3, qal_a, qal_b, qal_c, cy[h]);  // interface r-2: between rows r-3 (qw2) and r-2 (qw3)
+        qal_a = qal_b, qal_b = qal_c;
+        const T fyy = mul_rn(yf[h], fy2[h]);
+        // q_i of row r-3: interfaces r-3 (previous row) and r-2; q of row r-3 as stored, its area from the ring
         const T arj = ar_ring[(rr + 1) % RB];
-        const T ra = add_rn(arj, sub_rn(yf_prev, yf));
+        const T ra = add_rn(arj, sub_rn(yf_prev, yf[h]));
         qirow[par * PP + c] = mul_rn(fma_rn(q_m3, arj, sub_rn(fyy_prev, fyy)), rcp_fast_(ra));
-        fyy_prev = fyy, yf_prev = yf;
+        fyy_prev = fyy, yf_prev = yf[h];
+        q_st[h] = q_m3;                            // q of row r-3 as stored: the update of phase 5 starts from it
+        q_m3 = q_m2, q_m2 = q_m1, q_m1 = x0;
+        // rings: row r's values replace row r-4's (slot rr is not read again before that)
+        cxj[h] = cx_ring[(rr + 1) % RB], xfj[h] = xf_ring[(rr + 1) % RB], f2j[h] = fx2_ring[(rr + 1) % RB];
+        cx_ring[rr] = cx, xf_ring[rr] = xf, fx2_ring[rr] = fx2, ar_ring[rr] = ar_new[h];
       }
       __syncthreads();
-      // ---- 3. q_j of row r, outer y-sweep at interface r-2; thread = compute column ----
-      T fya;
-      {
-        const T xl = XFs[rr * WX + ccr], xh = XFs[rr * WX + ccr + 1];
-        const T ra = add_rn(ar_new, sub_rn(xl, xh));
-        const T num = fma_rn(q_new, ar_new, sub_rn(mul_rn(xl, fx2row[par * PP + ccr]), mul_rn(xh, fx2row[par * PP + ccr + 1])));
-        const T qj = mul_rn(num, rcp_fast_(ra));
-        jw0 = jw1, jw1 = jw2, jw2 = jw3, jw3 = jw4, jw4 = jw5, jw5 = qj;
-        const T jal_c = ppm_al(jw2, jw3, jw4, jw5);
-        const T fo = ppm_flux_from_al(jw2, jw3, jal_a, jal_b, jal_c, cy);
-        jal_a = jal_b, jal_b = jal_c;
-        fya = mul_rn(mul_rn(T(0.5), add_rn(fo, fy2)), yf);  // averaged y-flux at interface r-2
-        if (FLUX_OUT && fy_col && n >= 5 && n <= 5 + nrows) __stcs(fy_p, fya);  // interfaces jc0 .. jc1
+      // ---- phases 3 + 4 ----
+#pragma unroll
+      for (int h = 0; h < RP; ++h) {
+        const int rr = g * RP + h;
+        const int n = m * RB + rr;
+        const int par = rr & 1;
+        // 3. q_j of row r, outer y-sweep at interface r-2; thread = compute column
+        {
+          const T xl = XFs[rr * WX + ccr], xh = XFs[rr * WX + ccr + 1];
+          const T ra = add_rn(ar_new[h], sub_rn(xl, xh));
+          const T num = fma_rn(q_new[h], ar_new[h], sub_rn(mul_rn(xl, fx2row[par * PP + ccr]), mul_rn(xh, fx2row[par * PP + ccr + 1])));
+          const T qj = mul_rn(num, rcp_fast_(ra));
+          jw2 = jw3, jw3 = jw4, jw4 = jw5, jw5 = qj;  // q_j rows r-3 .. r
+          const T jal_c = ppm_al(jw2, jw3, jw4, jw5);
+          const T fo = ppm_flux_from_al(jw2, jw3, jal_a, jal_b, jal_c, cy[h]);
+          jal_a = jal_b, jal_b = jal_c;
+          fya[h] = mul_rn(mul_rn(T(0.5), add_rn(fo, fy2[h])), yf[h]);  // averaged y-flux at interface r-2
+          if (FLUX_OUT && fy_col && n >= 5 && n <= 5 + nrows) __stcs(fy_p, fya[h]);  // interfaces jc0 .. jc1
+        }
+        // 4. outer x-sweep of row r-3 on q_i; thread = interface
+        {
+          const T* qi = qirow + par * PP + c;
+          const T y0 = qi[0], y1 = qi[1], y2 = qi[2], y3 = qi[3], y4 = qi[4], y5 = qi[5];
+          const T fo = ppm_flux_from_al(y2, y3, ppm_al(y0, y1, y2, y3), ppm_al(y1, y2, y3, y4), ppm_al(y2, y3, y4, y5), cxj[h]);
+          const T fxa = mul_rn(mul_rn(T(0.5), add_rn(fo, f2j[h])), xfj[h]);
+          fxarow[par * PP + c] = fxa;
+          if (FLUX_OUT && fx_col && (unsigned)(n - 6) < (unsigned)nrows) __stcs(fx_p, fxa);
+        }
+        if (FLUX_OUT) fx_p += fx_sj, fy_p += fy_sj;
       }
-      // ---- 4. outer x-sweep of row r-3 on q_i; thread = interface ----
-      {
-        const T* qi = qirow + par * PP + c;
-        const T y0 = qi[0], y1 = qi[1], y2 = qi[2], y3 = qi[3], y4 = qi[4], y5 = qi[5];
-        const T cxj = cx_ring[(rr + 1) % RB], xfj = xf_ring[(rr + 1) % RB], f2j = fx2_ring[(rr + 1) % RB];
-        const T fo = ppm_flux_from_al(y2, y3, ppm_al(y0, y1, y2, y3), ppm_al(y1, y2, y3, y4), ppm_al(y2, y3, y4, y5), cxj);
-        const T fxa = mul_rn(mul_rn(T(0.5), add_rn(fo, f2j)), xfj);
-        fxarow[par * PP + c] = fxa;
-        if (FLUX_OUT && fx_col && (unsigned)(n - 6) < (unsigned)nrows) __stcs(fx_p, fxa);
-      }
-      // rings: this row's values replace row r-4's
-      cx_ring[rr] = cx, xf_ring[rr] = xf, fx2_ring[rr] = fx2, ar_ring[rr] = ar_new;
       __syncthreads();
-      // ---- 5. update of row r-3; thread = compute column ----
-      {
+      // ---- phase 5: update of rows r-3; thread = compute column ----
+#pragma unroll
+      for (int h = 0; h < RP; ++h) {
+        const int rr = g * RP + h;
+        const int n = m * RB + rr;
+        const int par = rr & 1;
         const T fxl = fxarow[par * PP + ccr], fxh = fxarow[par * PP + ccr + 1];
         if (store_col && (unsigned)(n - 6) < (unsigned)nrows)
-          __stcs(qo_p, fma_rn(ra_next, add_rn(sub_rn(fxl, fxh), sub_rn(fya_prev, fya)), q_m3));
-        fya_prev = fya;
-        // rarea of the row stored next iteration (r - 2), in flight across one iteration
-        if (store_col && (unsigned)(n - 5) < (unsigned)nrows) ra_next = __ldg(ra_p);
-        q_m3 = q_m2, q_m2 = q_m1, q_m1 = q_new;
-        qo_p += qo_sj, ra_p += ra_sj;
-        if (FLUX_OUT) fx_p += fx_sj, fy_p += fy_sj;
+          __stcs(qo_p, fma_rn(ra_row[h], add_rn(sub_rn(fxl, fxh), sub_rn(fya_prev, fya[h])), q_st[h]));
+        fya_prev = fya[h];
+        qo_p += qo_sj;
+      }
+      // rarea of the rows the next group stores (rows r-3 of iterations n+RP .. n+2RP-1), in flight across one group
+#pragma unroll
+      for (int h = 0; h < RP; ++h) {
+        const int n2 = m * RB + g * RP + h + RP;
+        if (store_col && (unsigned)(n2 - 6) < (unsigned)nrows) ra_row[h] = __ldg(ra_p);
+        ra_p += ra_sj;
       }
     }
     // every read of this stage is behind the last barrier of its last row: refill it with chunk m + 2
@@ -283,13 +307,16 @@ int launch_stream(int ni, int nj, int nk, int nb, F3<const T> q, F3<const T> crx
       make_map<T>(&myx, fyx.base, yfx.sj, yfx.sk, yfx.sb, ni + 6 + fyx.off, nj + 1, nk, nb, G::WQ, RB);
   if (!ok) return B2S_OK;
   const bool flux_out = fxo.p != nullptr || fyo.p != nullptr;
-  auto kern = flux_out ? k_fv_split_stream<T, TI, true> : k_fv_split_stream<T, TI, false>;
-  static bool configured[2] = {false, false};
-  if (!configured[flux_out]) {
+  // rows per barrier pair: b2s_set_option("fv_split_rp", 1 | 2); the flux-output variant stays at 1 (registers)
+  const int rp = flux_out ? 1 : (option("fv_split_rp", 0) == 1 ? 1 : 2);
+  auto kern = flux_out ? k_fv_split_stream<T, TI, true, 1> : (rp == 2 ? k_fv_split_stream<T, TI, false, 2> : k_fv_split_stream<T, TI, false, 1>);
+  static bool configured[3] = {false, false, false};
+  const int slot = flux_out ? 2 : rp - 1;
+  if (!configured[slot]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (e != cudaSuccess) return set_error((int)e, "fv_tp2d_split(stream): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    configured[flux_out] = true;
+    configured[slot] = true;
   }
   StreamParams<T> P;
   P.ni = ni, P.nj = nj, P.nk = nk;

@@ -48,7 +48,18 @@ __device__ __forceinline__ double rcp_(double x) {
   e = __fma_rn(-x, r, 1.0);
   return __fma_rn(r, e, r);
 }
-__device__ __forceinline__ float rcp_(float x) { return __frcp_rn(x); }
+__device__ __forceinline__ float rcp_(float x) {  // MUFU.RCP, <= 1 ulp: the IEEE-rounded __frcp_rn costs ~8 instructions
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// fp64 fmax / fmin compile to seven instructions each (DSETP.MAX + the NaN-propagation selects); a compare and a
+// select is three.  Operands here are never NaN (finite inputs, reciprocals of positive thicknesses).
+__device__ __forceinline__ double max_(double a, double b) { return a > b ? a : b; }
+__device__ __forceinline__ double min_(double a, double b) { return a < b ? a : b; }
+__device__ __forceinline__ float max_(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ float min_(float a, float b) { return fminf(a, b); }
 
 template <typename T>
 __device__ __forceinline__ T sgn_(T a, T b) {  // Fortran SIGN(a, b)
@@ -75,8 +86,8 @@ __device__ __forceinline__ void ppm_limit(T dm, T q, T& al, T& ar, int lmt) {
     }
   } else if (lmt == 1) {
     const T qmp = T(2) * dm;
-    al = q - sgn_(fmin(fabs(qmp), fabs(al - q)), qmp);
-    ar = q + sgn_(fmin(fabs(qmp), fabs(ar - q)), qmp);
+    al = q - sgn_(min_(fabs(qmp), fabs(al - q)), qmp);
+    ar = q + sgn_(min_(fabs(qmp), fabs(ar - q)), qmp);
   } else {
     if (fabs(ar - al) < -a6) {
       const T d = ar - al;
@@ -94,6 +105,17 @@ __device__ __forceinline__ void ppm_limit(T dm, T q, T& al, T& ar, int lmt) {
       }
     }
   }
+}
+
+// 4th-order interface value between layers k-1 and k (2 <= k <= km-2):
+//   d_m2 .. d_p1 = delp[k-2 .. k+1], qm = q[k-1], q0 = q[k], dcm = dc[k-1], dc0 = dc[k]
+template <typename T>
+__device__ __forceinline__ T ppm_iface(T d_m2, T dpm, T dp0, T d_p1, T qm, T q0, T dcm, T dc0) {
+  const T d4m = d_m2 + dpm, d4k = dpm + dp0, d4p = dp0 + d_p1;  // d4[k-1], d4[k], d4[k+1]
+  const T c1 = (q0 - qm) * dpm * rcp_(d4k);
+  const T a1 = d4m * rcp_(d4k + dpm);
+  const T a2 = d4p * rcp_(d4k + dp0);
+  return qm + c1 + T(2) * rcp_(d4m + d4p) * (dp0 * (c1 * (a1 - a2) + a2 * dcm) - dpm * a1 * dc0);
 }
 
 struct PpmLayout {
@@ -182,93 +204,145 @@ __global__ void __launch_bounds__(kThreads, MINB) k_remap_ppm(const __grid_const
     __syncthreads();
   }
 
-  // ---- 3. PPM profile in shared memory: thread = (column, level range) ----
+  // ---- 3. PPM profile in shared memory: thread = (column, contiguous level range [ka, kb)) ----
+  // Two marching sweeps with the windows in registers (one new edge, one new mean per level; rcp(d4[k+1]) of a
+  // slope is rcp(d4[k]) of the next one):  3.1 slopes dc -> slab A;  3.2 interface value k+1 by the 4th-order
+  // formula, then ppm_limiters of layer k, AL -> slab A (over dc[k], no longer needed), AR -> slab B.  The two top
+  // and two bottom layers (area-preserving cubics, standard constraint) are built by the level ranges 0 and 1
+  // from the slabs.  The first version kept dc and the interface values in slabs between four phases with
+  // strided level ownership: 7 reciprocals and ~280 instructions per layer (profiles/r01_next_rows.md).
   {
     const int col = threadIdx.x % COLS, kl = threadIdx.x / COLS;
     const T* Ec = E + col + (LOADER == 2 ? P.off_e : 0);
     const T* Qc = Q + col + (LOADER == 2 ? P.off_q : 0);
     T* Ac = A + col;
     T* Bc = B + col;
-    // 3.1 monotonised slopes, k = 1 .. km-2
-    for (int k = 1 + kl; k < km - 1; k += NKL) {
-      const T e0 = Ec[(k - 1) * PITCH], e1 = Ec[k * PITCH], e2_ = Ec[(k + 1) * PITCH], e3 = Ec[(k + 2) * PITCH];
-      const T dm = e1 - e0, d0 = e2_ - e1, dp = e3 - e2_;  // delp[k-1], delp[k], delp[k+1]
-      const T qm = Qc[(k - 1) * PITCH], q0 = Qc[k * PITCH], qp = Qc[(k + 1) * PITCH];
-      const T d4k = dm + d0, d4p = d0 + dp;
-      const T c1 = (dm + T(0.5) * d0) * rcp_(d4p);
-      const T c2 = (dp + T(0.5) * d0) * rcp_(d4k);
-      const T df2 = d0 * (c1 * (qp - q0) + c2 * (q0 - qm)) * rcp_(d4k + dp);
-      const T qmax = fmax(fmax(qm, q0), qp) - q0;
-      const T qmin = q0 - fmin(fmin(qm, q0), qp);
-      Ac[k * PITCH] = sgn_(fmin(fmin(fabs(df2), qmax), qmin), df2);
+    const int per = (km + NKL - 1) / NKL;
+    const int ka = min(km, kl * per), kb = min(km, ka + per);
+    // 3.1 monotonised slopes dc[k], k in [ka, kb) and 1 .. km-2
+    {
+      const int ks = max(ka, 1), ke = min(kb, km - 1);
+      if (ks < ke) {
+        const T* ep = Ec + (ks - 1) * PITCH;
+        const T* qp_ = Qc + (ks - 1) * PITCH;
+        T* ap = Ac + ks * PITCH;
+        T e2_ = ep[2 * PITCH];
+        T dm = ep[PITCH] - ep[0], d0 = e2_ - ep[PITCH];  // delp[k-1], delp[k]
+        T qm = qp_[0], q0 = qp_[PITCH];
+        T r4k = rcp_(dm + d0);
+        ep += 3 * PITCH, qp_ += 2 * PITCH;
+#pragma unroll 3
+        for (int k = ks; k < ke; ++k) {
+          const T e3 = ep[0], qp = qp_[0];
+          const T dp = e3 - e2_;  // delp[k+1]
+          const T d4k = dm + d0, d4p = d0 + dp;
+          const T r4p = rcp_(d4p);
+          const T c1 = (dm + T(0.5) * d0) * r4p;
+          const T c2 = (dp + T(0.5) * d0) * r4k;
+          const T df2 = d0 * (c1 * (qp - q0) + c2 * (q0 - qm)) * rcp_(d4k + dp);
+          const T qmax = max_(max_(qm, q0), qp) - q0;
+          const T qmin = q0 - min_(min_(qm, q0), qp);
+          ap[0] = sgn_(min_(min_(fabs(df2), qmax), qmin), df2);
+          dm = d0, d0 = dp, e2_ = e3, qm = q0, q0 = qp, r4k = r4p;
+          ep += PITCH, qp_ += PITCH, ap += PITCH;
+        }
+      }
     }
     __syncthreads();
-    // 3.2 interior interface values, k = 2 .. km-2
-    for (int k = 2 + kl; k < km - 1; k += NKL) {
+    // interface value k (2 <= k <= km-2) from the slabs: the start of a march, and the cubics' anchor
+    auto iface = [&](int k) -> T {
       const T e0 = Ec[(k - 2) * PITCH], e1 = Ec[(k - 1) * PITCH], e2_ = Ec[k * PITCH], e3 = Ec[(k + 1) * PITCH], e4 = Ec[(k + 2) * PITCH];
-      const T dpm = e2_ - e1, dp0 = e3 - e2_;                  // delp[k-1], delp[k]
-      const T d4m = (e1 - e0) + dpm, d4k = dpm + dp0, d4p = dp0 + (e4 - e3);  // d4[k-1], d4[k], d4[k+1]
-      const T qm = Qc[(k - 1) * PITCH], q0 = Qc[k * PITCH];
-      const T c1 = (q0 - qm) * dpm * rcp_(d4k);
-      const T a1 = d4m * rcp_(d4k + dpm);
-      const T a2 = d4p * rcp_(d4k + dp0);
-      Bc[k * PITCH] = qm + c1 + T(2) * rcp_(d4m + d4p) * (dp0 * (c1 * (a1 - a2) + a2 * Ac[(k - 1) * PITCH]) - dpm * a1 * Ac[k * PITCH]);
+      return ppm_iface<T>(e1 - e0, e2_ - e1, e3 - e2_, e4 - e3, Qc[(k - 1) * PITCH], Qc[k * PITCH], Ac[(k - 1) * PITCH], Ac[k * PITCH]);
+    };
+    int lmt = max(0, P.kord - 3);
+    if (P.iv == 0) lmt = min(2, lmt);
+    // everything that reads a dc another thread will overwrite with AL comes first ...
+    const int ga = max(ka, 2), gb = min(kb, km - 2);  // generic layers of this range: both interfaces interior
+    T a_k = T(0), dc_k = T(0), dc_end = T(0);
+    if (ga < gb) {
+      a_k = iface(ga);             // reads dc[ga-1] (the previous range's when ga == ka)
+      dc_k = Ac[ga * PITCH];
+      dc_end = Ac[gb * PITCH];     // dc of the next range's first layer (gb <= km-2: a slope exists)
     }
-    __syncthreads();
-    // 3.3 top and surface: area-preserving cubic with zero second derivative at the boundary
+    T bl0 = T(0), br0 = T(0), bl1 = T(0), br1 = T(0);  // (AL, AR) of the two boundary layers this thread builds
     if (kl == 0) {
+      // top: area-preserving cubic with zero second derivative at the boundary
       const T d1 = Ec[PITCH] - Ec[0], d2 = Ec[2 * PITCH] - Ec[PITCH];
       const T q0 = Qc[0], q1 = Qc[PITCH];
+      const T a2 = iface(2);
       const T r12 = rcp_(d1 + d2);
       const T qm = (d2 * q0 + d1 * q1) * r12;
       const T dq = T(2) * (q1 - q0) * r12;
-      const T c1 = T(4) * (Bc[2 * PITCH] - qm - d2 * dq) * rcp_(d2 * (T(2) * d2 * d2 + d1 * (d2 + T(3) * d1)));
+      const T c1 = T(4) * (a2 - qm - d2 * dq) * rcp_(d2 * (T(2) * d2 * d2 + d1 * (d2 + T(3) * d1)));
       const T c3 = dq - T(0.5) * c1 * (d2 * (T(5) * d1 + d2) - T(3) * d1 * d1);
       T al1 = qm - T(0.25) * c1 * d1 * d2 * (d2 + T(3) * d1);
       T al0 = d1 * (T(2) * c1 * d1 * d1 - c3) + al1;
-      al1 = fmax(al1, fmin(q0, q1));
-      al1 = fmin(al1, fmax(q0, q1));
-      Ac[0] = T(0.5) * (al1 - q0);
-      if (P.iv == 0) al0 = fmax(T(0), al0), al1 = fmax(T(0), al1);
-      Bc[0] = al0;
-      Bc[PITCH] = al1;
+      al1 = max_(al1, min_(q0, q1));
+      al1 = min_(al1, max_(q0, q1));
+      const T dc0 = T(0.5) * (al1 - q0);
+      if (P.iv == 0) al0 = max_(T(0), al0), al1 = max_(T(0), al1);
+      bl0 = al0, br0 = al1;
+      ppm_limit<T>(dc0, q0, bl0, br0, 0);
+      bl1 = al1, br1 = a2;
+      ppm_limit<T>(Ac[PITCH], q1, bl1, br1, 0);
     } else if (kl == 1) {
+      // surface: the same cubic; bl0/br0 = layer km-2, bl1/br1 = layer km-1
       const T d1 = Ec[km * PITCH] - Ec[(km - 1) * PITCH], d2 = Ec[(km - 1) * PITCH] - Ec[(km - 2) * PITCH];
       const T q0 = Qc[(km - 1) * PITCH], q1 = Qc[(km - 2) * PITCH];
+      const T a2 = iface(km - 2);
       const T r12 = rcp_(d1 + d2);
       const T qm = (d2 * q0 + d1 * q1) * r12;
       const T dq = T(2) * (q1 - q0) * r12;
-      const T c1 = (Bc[(km - 2) * PITCH] - qm - d2 * dq) * rcp_(d2 * (T(2) * d2 * d2 + d1 * (d2 + T(3) * d1)));
+      const T c1 = (a2 - qm - d2 * dq) * rcp_(d2 * (T(2) * d2 * d2 + d1 * (d2 + T(3) * d1)));
       const T c3 = dq - T(2) * c1 * (d2 * (T(5) * d1 + d2) - T(3) * d1 * d1);
       T alb = qm - c1 * d1 * d2 * (d2 + T(3) * d1);
       T arb = d1 * (T(8) * c1 * d1 * d1 - c3) + alb;
-      alb = fmax(alb, fmin(q0, q1));
-      alb = fmin(alb, fmax(q0, q1));
-      Ac[(km - 1) * PITCH] = T(0.5) * (q0 - alb);
-      if (P.iv == 0) alb = fmax(T(0), alb), arb = fmax(T(0), arb);
-      Bc[(km - 1) * PITCH] = alb;
-      Bc[km * PITCH] = arb;
+      alb = max_(alb, min_(q0, q1));
+      alb = min_(alb, max_(q0, q1));
+      const T dcb = T(0.5) * (q0 - alb);
+      if (P.iv == 0) alb = max_(T(0), alb), arb = max_(T(0), arb);
+      bl0 = a2, br0 = alb;
+      ppm_limit<T>(Ac[(km - 2) * PITCH], q1, bl0, br0, 0);
+      bl1 = alb, br1 = arb;
+      ppm_limit<T>(dcb, q0, bl1, br1, 0);
     }
     __syncthreads();
-    // 3.4 limiters on a contiguous level range [ka, kb): AL over dc, AR over the interface values.  The
-    // interface kb is also the left edge of the next range, whose owner overwrites it: save it first.
-    const int per = (km + NKL - 1) / NKL;
-    const int ka = min(km, kl * per), kb = min(km, ka + per);
-    const T ir_last = Bc[kb * PITCH];
-    __syncthreads();
-    int lmt = max(0, P.kord - 3);
-    if (P.iv == 0) lmt = min(2, lmt);
-    for (int k = ka; k < kb; ++k) {
-      T al = Bc[k * PITCH];
-      T ar = k + 1 < kb ? Bc[(k + 1) * PITCH] : ir_last;
-      ppm_limit<T>(Ac[k * PITCH], Qc[k * PITCH], al, ar, (k < 2 || k >= km - 2) ? 0 : lmt);
-      Ac[k * PITCH] = al;
-      Bc[k * PITCH] = ar;
+    // ... then the stores
+    if (kl == 0) {
+      Ac[0] = bl0, Bc[0] = br0, Ac[PITCH] = bl1, Bc[PITCH] = br1;
+    } else if (kl == 1) {
+      Ac[(km - 2) * PITCH] = bl0, Bc[(km - 2) * PITCH] = br0, Ac[(km - 1) * PITCH] = bl1, Bc[(km - 1) * PITCH] = br1;
+    }
+    // 3.2 march over the generic layers: interface k+1, then the limiter of layer k
+    if (ga < gb) {
+      const T* ep = Ec + (ga - 1) * PITCH;
+      const T* qp_ = Qc + ga * PITCH;
+      T* ap = Ac + ga * PITCH;
+      T* bp = Bc + ga * PITCH;
+      T e_n = ep[3 * PITCH];                                          // edge k+2
+      T dA = ep[PITCH] - ep[0], dB = ep[2 * PITCH] - ep[PITCH], dC = e_n - ep[2 * PITCH];  // delp[k-1], delp[k], delp[k+1]
+      T q_k = qp_[0];
+      ep += 4 * PITCH, qp_ += PITCH;
+#pragma unroll 3
+      for (int k = ga; k < gb; ++k) {
+        const T e_nn = ep[0];             // edge k+3
+        const T q_1 = qp_[0];             // q[k+1]
+        const T dc_1 = k + 1 < gb ? ap[PITCH] : dc_end;  // dc[k+1]; slab A holds dc above this thread's stores
+        const T dD = e_nn - e_n;          // delp[k+2]
+        const T a_1 = ppm_iface<T>(dA, dB, dC, dD, q_k, q_1, dc_k, dc_1);
+        T al = a_k, ar = a_1;
+        ppm_limit<T>(dc_k, q_k, al, ar, lmt);
+        ap[0] = al, bp[0] = ar;
+        dA = dB, dB = dC, dC = dD, e_n = e_nn, q_k = q_1, dc_k = dc_1, a_k = a_1;
+        ep += PITCH, qp_ += PITCH, ap += PITCH, bp += PITCH;
+      }
     }
     __syncthreads();
   }
 
   // ---- 4. map1_ppm: integrate the parabolas over the target layers of this thread's chunks ----
+  // The source layer under the top edge (edges, AL, AR, mean, A6, 1/dp) is carried in registers from one target
+  // layer to the next: a target layer that ends in source layer m leaves exactly that state behind.
   const T* El = E + mcol + (LOADER == 2 ? P.off_e : 0);
   const T* Ql = Q + mcol + (LOADER == 2 ? P.off_q : 0);
   const T* Al = A + mcol;
@@ -286,15 +360,19 @@ __global__ void __launch_bounds__(kThreads, MINB) k_remap_ppm(const __grid_const
       }
       l = a;
     }
+    T e0 = El[l * PITCH], e1 = El[(l + 1) * PITCH];
+    T al = Al[l * PITCH], ar = Bl[l * PITCH];
+    T a6, rdp;
+    {
+      const T qv = Ql[l * PITCH];
+      a6 = T(3) * (T(2) * qv - (al + ar));
+      rdp = rcp_(e1 - e0);
+    }
     T* op = o2;
 #pragma unroll
     for (int u = 0; u < CH; ++u) {
       if (u < nlev) {
         const T top = tgt[u], bot = tgt[u + 1];
-        const T e0 = El[l * PITCH], e1 = El[(l + 1) * PITCH];
-        const T al = Al[l * PITCH], ar = Bl[l * PITCH], qv = Ql[l * PITCH];
-        const T a6 = T(3) * (T(2) * qv - (al + ar));
-        const T rdp = rcp_(e1 - e0);
         const T pl = (top - e0) * rdp;
         T res;
         if (bot <= e1) {  // the target layer lies inside source layer l
@@ -303,19 +381,22 @@ __global__ void __launch_bounds__(kThreads, MINB) k_remap_ppm(const __grid_const
         } else {
           T qsum = (e1 - top) * (al + half * (a6 + ar - al) * (one + pl) - a6 * (r3 * (one + pl * (one + pl))));
           T em = e1;
+          const T* ep = El + (l + 2) * PITCH;
           for (int m = l + 1; m < km; ++m) {
-            const T em1 = El[(m + 1) * PITCH];
+            const T em1 = ep[0];
             const T qm = Ql[m * PITCH];
             if (bot > em1) {  // whole layer
               qsum = qsum + (em1 - em) * qm;
               em = em1;
+              ep += PITCH;
             } else {
               const T alm = Al[m * PITCH], arm = Bl[m * PITCH];
               const T a6m = T(3) * (T(2) * qm - (alm + arm));
               const T dp = bot - em;
-              const T esl = dp * rcp_(em1 - em);
+              const T rdm = rcp_(em1 - em);
+              const T esl = dp * rdm;
               qsum = qsum + dp * (alm + half * esl * (arm - alm + a6m * (one - r23 * esl)));
-              l = m;
+              l = m, e0 = em, e1 = em1, al = alm, ar = arm, a6 = a6m, rdp = rdm;
               break;
             }
           }
@@ -365,7 +446,9 @@ int dispatch_ppm(int loader, const CUtensorMap& me, const CUtensorMap& mq, const
   // (16-column CTAs have 16 chunks: CH = 5 for nk2 <= 80, 9 for nk2 <= 144; 32-column CTAs have 8)
   constexpr int NCHUNK = 8 * (32 / COLS);
   const int ch = P.nk2 <= NCHUNK * 5 ? 5 : (P.nk2 <= NCHUNK * 9 ? 9 : 18);
-#define B2S_PPM(CH, LOADER) launch_ppm<T, COLS, CH, LOADER, 2>(me, mq, P, nj, nb, s)
+  // three CTAs per SM whenever their slabs fit (registers capped at 85 by the launch bounds), else two
+  const bool three = 3 * ((size_t)PpmLayout(P.nk1, (COLS + (loader == 2 ? 16 / (int)sizeof(T) : 0)) * (int)sizeof(T)).total + 1024) <= (size_t)227 * 1024;
+#define B2S_PPM(CH, LOADER) (three ? launch_ppm<T, COLS, CH, LOADER, 3>(me, mq, P, nj, nb, s) : launch_ppm<T, COLS, CH, LOADER, 2>(me, mq, P, nj, nb, s))
 #define B2S_PPM_CH(LOADER) (ch == 5 ? B2S_PPM(5, LOADER) : (ch == 9 ? B2S_PPM(9, LOADER) : B2S_PPM(18, LOADER)))
   if (loader == 0) return B2S_PPM_CH(0);
   if (loader == 2) return B2S_PPM_CH(2);
