@@ -359,6 +359,22 @@ def test_fv_tp2d_split(st, corc, shape, ti, variant, jb, dtype):
         assert torch.equal(out, tile) and torch.equal(fx, tfx) and torch.equal(fy, tfy)
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_fv_tp2d_split_rows_per_barrier_pair(st, dtype):
+    """Streaming kernel, one or two rows between barriers (fv_split_rp): same bits."""
+    from b200stencil import _abi
+
+    f = gen.fv_split_inputs(70, 23, 2, dtype)
+    outs = []
+    for rp in (1, 2):
+        _abi.set_option("fv_split_rp", rp)
+        try:
+            outs.append(_split_call(st, f, 2, dtype, False, 0, variant=2, jb=7)[0])
+        finally:
+            _abi.set_option("fv_split_rp", 0)
+    assert torch.equal(outs[0], outs[1])
+
+
 @pytest.mark.parametrize("shape", [(12, 9, 3), (70, 11, 2), (130, 20, 1)])
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_fv_tp2d_split_cube_corners(st, corc, shape, dtype):
