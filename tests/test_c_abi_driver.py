@@ -1,0 +1,53 @@
+"""A compiled C program calls libb200stencil through include/b200stencil.h with no Python in the process
+(tests/c_abi/abi_driver.c) -- the counterpart of the reference's acceptance program for its generated bridge
+(test/py_ftn_interface/data/fortran_program.f90:24-36).  Without a GPU the program must fail loudly at
+b2s_init (no CPU fallback); on the B200 it must reproduce the reference's golden vectors."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "c_abi", "abi_driver.c")
+LIBDIR = os.path.join(ROOT, "geosongpu-ci_b200", "b200stencil", "lib")
+CUDA = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+
+
+@pytest.fixture(scope="module")
+def driver(tmp_path_factory):
+    if shutil.which("gcc") is None or not os.path.exists(os.path.join(CUDA, "include", "cuda_runtime_api.h")):
+        pytest.skip("gcc or the CUDA runtime headers are not available")
+    if not os.path.exists(os.path.join(LIBDIR, "libb200stencil.so")):
+        pytest.fail("libb200stencil.so is not built: run python __graft_entry__.py")
+    exe = str(tmp_path_factory.mktemp("c_abi") / "abi_driver")
+    cmd = ["gcc", "-O1", "-Wall", "-Wextra", "-Werror", SRC, "-I", os.path.join(ROOT, "include"), "-I", os.path.join(CUDA, "include"),
+           "-L", LIBDIR, "-lb200stencil", "-L", os.path.join(CUDA, "lib64"), "-lcudart", "-o", exe]  # fmt: skip
+    subprocess.run(cmd, check=True, capture_output=True, text=True)
+    env = dict(os.environ, LD_LIBRARY_PATH=os.pathsep.join([LIBDIR, os.path.join(CUDA, "lib64"), os.environ.get("LD_LIBRARY_PATH", "")]))
+    return exe, env
+
+
+def _has_cuda():
+    try:
+        import torch
+
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_has_cuda(), reason="this is the no-GPU behaviour")
+def test_compiled_caller_fails_loudly_without_a_gpu(driver):
+    exe, env = driver
+    r = subprocess.run([exe], env=env, capture_output=True, text=True, timeout=60)
+    assert r.returncode == 3, (r.returncode, r.stdout, r.stderr)
+    assert "b2s_init" in r.stderr and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+def test_compiled_caller_reproduces_the_golden_vectors(driver):
+    exe, env = driver
+    r = subprocess.run([exe], env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "abi_driver ok" in r.stdout
