@@ -378,14 +378,14 @@ def main(argv=None) -> int:
     if tr.overlap:
         r = tr.interior
         kernel_points = nsub * (r[1] - r[0]) * (r[3] - r[2]) * NK
-        kernel_name = "k_fv_tma (interior rectangle launch)"
+        kernel_name = "k_fv_stream (interior rectangle launch)"
     else:
         kernel_points = local_points
-        kernel_name = "k_fv_tma (full-domain launch)"
+        kernel_name = "k_fv_stream (full-domain launch)"
     kbytes = kernel_points * algorithmic_bytes_per_point(es)
     achieved = kbytes / (kernel_ms * 1e-3) / 1e9
     traffic = None
-    prof = os.path.join(ROOT, "profiles", "fv_tma_traffic.json")
+    prof = os.path.join(ROOT, "profiles", "fv_stream_traffic.json")  # ncu --set full capture of the same launch
     if os.path.exists(prof) and not tr.overlap:
         with open(prof) as f:
             traffic = json.load(f).get(ns.dtype, {}).get("dram_bytes_per_launch")

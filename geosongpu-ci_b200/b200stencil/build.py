@@ -32,6 +32,7 @@ SOURCES = {
     "k_fv.cu": [],
     "k_fv_direct.cu": [],
     "k_fv_tma.cu": [],
+    "k_fv_stream.cu": [],
     "tma_host.cu": [],
     "k_fv_split.cu": [],
     "k_fv_split_stream.cu": [],

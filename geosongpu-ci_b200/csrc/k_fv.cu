@@ -13,6 +13,11 @@ int fv_tp2d_tma(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j1, 
                 bool* applicable);
 
 template <typename T>
+int fv_tp2d_stream(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j1, F3<const T> q, F3<const T> crx,
+                   F3<const T> xfx, F3<const T> cry, F3<const T> yfx, F2<const T> rarea, F3<T> q_out, cudaStream_t s,
+                   bool* applicable);
+
+template <typename T>
 int fv_tp2d(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j1, F3<const T> q, F3<const T> crx,
             F3<const T> xfx, F3<const T> cry, F3<const T> yfx, F2<const T> rarea, F3<T> q_out, cudaStream_t s) {
   B2S_ARGCHECK(ni > 0 && nj > 0 && nk > 0 && nb > 0, "fv_tp2d: empty domain %dx%dx%dx%d", ni, nj, nk, nb);
@@ -21,6 +26,17 @@ int fv_tp2d(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j1, F3<c
   B2S_ARGCHECK(q.p && crx.p && xfx.p && cry.p && yfx.p && rarea.p && q_out.p, "fv_tp2d: null field");
   if (i0 == i1 || j0 == j1) return B2S_OK;
   const int variant = option("fv_variant", 0);
+  // auto: the streaming kernel (every row staged once; 453 us against the tile kernel's 516 us on C384x72 fp64,
+  // 237 against 282 us on 3 x 384 x 384 x 72), except for launches below ~12 M points where the tile kernel's
+  // finer work items fill the machine better (3 x 192 x 192 x 72, the 8-GPU sub-domains: 61.0 against 63.1 us);
+  // the tile kernel as the second TMA choice, the direct kernel for fields TMA cannot address
+  const bool small = (int64_t)(i1 - i0) * (j1 - j0) * nk * nb < 12000000;
+  if (variant == 3 || (variant == 0 && !small)) {
+    bool applicable = false;
+    int rc = fv_tp2d_stream<T>(ni, nj, nk, nb, i0, i1, j0, j1, q, crx, xfx, cry, yfx, rarea, q_out, s, &applicable);
+    if (applicable) return rc;
+    if (variant == 3) return set_error(B2S_EUNSUPPORTED, "fv_tp2d: fv_variant=3 forced but fields do not meet the TMA alignment rules");
+  }
   if (variant != 1) {
     bool applicable = false;
     int rc = fv_tp2d_tma<T>(ni, nj, nk, nb, i0, i1, j0, j1, q, crx, xfx, cry, yfx, rarea, q_out, s, &applicable);

@@ -241,7 +241,7 @@ def _fv_case(st, corc, ni, nj, nk, dtype, variant=0, region=None, align=True):
 
 @pytest.mark.parametrize("shape", [(3, 3, 4), (24, 24, 8), (13, 7, 5), (1, 1, 2), (130, 20, 3), (128, 64, 2), (300, 9, 2)])
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 3])
 def test_fv_tp2d(st, corc, shape, dtype, variant):
     _fv_case(st, corc, *shape, dtype, variant=variant)
 
@@ -256,18 +256,28 @@ def test_fv_tp2d_variants_bit_identical(st, dtype):
     d = {k: up(v) for k, v in f.items()}
     outs = []
     combos = [(1, 0, 0, 0)] + [(2, ti, r, st) for ti in (32, 64, 96, 128, 192) for r, st in ((4, 2), (8, 3))]
+    # streaming kernel (variant 3): strip widths, ring depths, rows per item (5 and 16 put item boundaries inside the domain)
+    combos += [(3, ti, jb, st) for ti in (32, 64, 128) for jb, st in ((0, 2), (5, 3), (16, 4))]
     for variant, ti, rows, stages in combos:
-        for name, v in (("fv_variant", variant), ("fv_ti", ti), ("fv_rows", rows), ("fv_stages", stages)):
+        for name, v in (("fv_variant", variant), ("fv_ti", ti), ("fv_rows", rows if variant == 2 else 0),
+                        ("fv_jb", rows if variant == 3 else 0), ("fv_stages", stages)):
             _abi.set_option(name, v)
         try:
             out = up(np.zeros((ni, nj, nk), dtype))
             st.fv_tp2d(d["q"], d["crx"], d["xfx"], d["cry"], d["yfx"], d["rarea"], out)
             outs.append(down(out))
         finally:
-            for name in ("fv_variant", "fv_ti", "fv_rows", "fv_stages"):
+            for name in ("fv_variant", "fv_ti", "fv_rows", "fv_jb", "fv_stages"):
                 _abi.set_option(name, 0)
     for o in outs[1:]:
         assert np.array_equal(o, outs[0])
+
+
+def test_fv_tp2d_streaming_regions(st, corc):
+    _fv_case(st, corc, 40, 30, 3, np.float64, 3, region=(3, 37, 3, 27))
+    _fv_case(st, corc, 40, 30, 3, np.float64, 3, region=(0, 40, 0, 3))
+    _fv_case(st, corc, 40, 30, 3, np.float32, 3, region=(37, 40, 3, 27))
+    _fv_case(st, corc, 200, 150, 2, np.float64, 3)  # several strips, two row blocks
 
 
 @pytest.mark.parametrize("variant", [0, 1])
