@@ -386,7 +386,7 @@ def main(argv=None) -> int:
     achieved = kbytes / (kernel_ms * 1e-3) / 1e9
     traffic = None
     prof = os.path.join(ROOT, "profiles", "fv_stream_traffic.json")  # ncu --set full capture of the same launch
-    if os.path.exists(prof) and not tr.overlap:
+    if os.path.exists(prof) and not tr.overlap and n_gpus == 1:  # the capture is of the N = 1 launch (6 x 384 x 384 x 72)
         with open(prof) as f:
             traffic = json.load(f).get(ns.dtype, {}).get("dram_bytes_per_launch")
     roofline = {

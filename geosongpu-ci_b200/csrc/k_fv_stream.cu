@@ -244,14 +244,26 @@ int launch_stream(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j1
   FvStreamParams<T> P;
   P.nk = nk, P.i0 = i0, P.i1 = i1, P.j0 = j0, P.j1 = j1;
   P.nstrips = (i1 - i0 + TI - 1) / TI;
-  // rows per item: the whole column height when that leaves at least ~8 items per SM for the persistent grid
-  // (C384x72 on one GPU: 1296 items of 384 rows, 453 us; 128-row items 477 us, 64-row items 519 us: the six
-  // warm-up rows of an item are overhead), else halved until it does; b2s_set_option("fv_jb", n) overrides
+  // Rows per item and grid size.  Items are long (a whole column height where possible: the six warm-up rows of
+  // an item are overhead -- C384x72 fp64: 453 us with 384-row items, 477 with 128, 519 with 64) and the persistent
+  // grid hands them out statically, so the split must come out even: for 1 .. 16 row blocks per column, model the
+  // busiest SM (waves of items per CTA x CTAs on that SM) and keep the best of  items / (SMs x that)  x  JB / (JB + 6).
+  // (fp32 C384x72 with one block: 1296 items on 888 CTAs = 1.46 per CTA, 267 us; two blocks: 248 us.)
+  // b2s_set_option("fv_jb", n) overrides the choice.
   const int h = j1 - j0;
+  const int64_t max_ctas = (int64_t)sm_count() * ctas_per_sm;
+  auto even_grid = [&](int64_t n) { const int64_t waves = (n + max_ctas - 1) / max_ctas; return (n + waves - 1) / waves; };
   int jb = option("fv_jb", 0);
   if (jb <= 0) {
-    jb = h < 1024 ? h : 1024;
-    while (jb > 32 && (int64_t)P.nstrips * ((h + jb - 1) / jb) * nk * nb < (int64_t)8 * sm_count()) jb = (jb + 1) / 2;
+    double best = -1.0;
+    for (int nb_j = 1; nb_j <= 16 && (nb_j == 1 || h / nb_j >= 32); ++nb_j) {
+      const int cand = (h + nb_j - 1) / nb_j;
+      const int64_t n = (int64_t)P.nstrips * ((h + cand - 1) / cand) * nk * nb;
+      const int64_t waves = (n + max_ctas - 1) / max_ctas, g = even_grid(n);
+      const int64_t busiest = (g + sm_count() - 1) / sm_count() * waves;
+      const double score = (double)n / ((double)sm_count() * busiest) * cand / (cand + 6.0);
+      if (score > best) best = score, jb = cand;
+    }
   }
   const int nblk_j = (h + jb - 1) / jb;
   P.jb = (h + nblk_j - 1) / nblk_j;
@@ -266,8 +278,7 @@ int launch_stream(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j1
   P.c_yfx = i0 + fyx.off, P.sh_yfx = P.c_yfx % V;
   P.rarea = rarea;
   P.qout = q_out;
-  const int64_t max_ctas = (int64_t)sm_count() * ctas_per_sm;
-  const int grid = (int)(nitems < max_ctas ? nitems : max_ctas);
+  const int grid = (int)even_grid(nitems);
   *applicable = true;
   kern<<<grid, G::THREADS, G::SMEM_BYTES, s>>>(mq, mcx, mxx, mcy, myx, P);
   return check_launch("fv_tp2d(stream)");
