@@ -30,7 +30,8 @@ int fv_tp2d(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j1, F3<c
   // 237 against 282 us on 3 x 384 x 384 x 72), except for launches below ~12 M points where the tile kernel's
   // finer work items fill the machine better (3 x 192 x 192 x 72, the 8-GPU sub-domains: 61.0 against 63.1 us);
   // the tile kernel as the second TMA choice, the direct kernel for fields TMA cannot address
-  const bool small = (int64_t)(i1 - i0) * (j1 - j0) * nk * nb < 12000000;
+  const int64_t small_below = option("fv_small_points", 0) > 0 ? (int64_t)option("fv_small_points", 0) : 12000000;
+  const bool small = (int64_t)(i1 - i0) * (j1 - j0) * nk * nb < small_below;
   if (variant == 3 || (variant == 0 && !small)) {
     bool applicable = false;
     int rc = fv_tp2d_stream<T>(ni, nj, nk, nb, i0, i1, j0, j1, q, crx, xfx, cry, yfx, rarea, q_out, s, &applicable);

@@ -292,14 +292,25 @@ template <typename T>
 int fv_tp2d_stream(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j1, F3<const T> q, F3<const T> crx,
                    F3<const T> xfx, F3<const T> cry, F3<const T> yfx, F2<const T> rarea, F3<T> q_out, cudaStream_t s,
                    bool* applicable) {
-  // strip width: 128 columns, 64 where that wastes fewer (the 192-wide sub-domains of the 8-GPU layout), 32 for
-  // narrow rectangles; ring depth b2s_set_option("fv_stages", 2 | 3 | 4)
+  // strip width: the one of 128 / 96 / 64 columns that pads the rectangle least, the wider on ties (192-wide
+  // sub-domains of the 8-GPU layout: two 96-column strips), 32 for narrow rectangles; ring depth
+  // b2s_set_option("fv_stages", 2 | 3 | 4) for the 128- and 64-column kernels
   const int w = i1 - i0;
   int ti = option("fv_ti", 0);
-  if (ti != 32 && ti != 64 && ti != 128) ti = w <= 32 ? 32 : ((w + 127) / 128 * 128 - w > (w + 63) / 64 * 64 - w ? 64 : 128);
+  if (ti != 32 && ti != 64 && ti != 96 && ti != 128) {
+    ti = 32;
+    if (w > 32) {
+      int best_waste = 1 << 30;
+      for (int c : {128, 96, 64}) {
+        const int waste = (w + c - 1) / c * c - w;
+        if (waste < best_waste) best_waste = waste, ti = c;
+      }
+    }
+  }
   int stages = option("fv_stages", 0);
   if (stages < 2 || stages > 4) stages = 3;
   if (ti == 32) return launch_stream<T, 32, 4>(B2S_FVS_ARGS);
+  if (ti == 96) return launch_stream<T, 96, 3>(B2S_FVS_ARGS);
   if (ti == 64) return stages == 2 ? launch_stream<T, 64, 2>(B2S_FVS_ARGS) : (stages == 4 ? launch_stream<T, 64, 4>(B2S_FVS_ARGS) : launch_stream<T, 64, 3>(B2S_FVS_ARGS));
   return stages == 2 ? launch_stream<T, 128, 2>(B2S_FVS_ARGS) : (stages == 4 ? launch_stream<T, 128, 4>(B2S_FVS_ARGS) : launch_stream<T, 128, 3>(B2S_FVS_ARGS));
 }

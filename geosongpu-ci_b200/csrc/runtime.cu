@@ -21,6 +21,7 @@ static int g_sms = 0;
 static std::mutex g_mu;
 static std::map<std::string, int> g_options = {
     {"fv_variant", 0},      // 0 auto (3, else 2, else 1), 1 direct (L1/L2) kernel, 2 TMA-pipelined tile kernel, 3 TMA streaming kernel (k_fv_stream.cu)
+    {"fv_small_points", 0}, // auto choice: launches below this many points use the tile kernel, 0 = 12 000 000
     {"fv_jb", 0},           // streaming kernel: rows per work item, 0 auto (column height, halved until >= 8 items per SM)
     {"fv_ti", 0},           // TMA tile width: 0 auto, 32 | 64 | 96 | 128 | 192 (k_fv_tma.cu)
     {"fv_rows", 0},         // rows per stage: 0 auto, 4 | 8

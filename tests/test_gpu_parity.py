@@ -257,7 +257,7 @@ def test_fv_tp2d_variants_bit_identical(st, dtype):
     outs = []
     combos = [(1, 0, 0, 0)] + [(2, ti, r, st) for ti in (32, 64, 96, 128, 192) for r, st in ((4, 2), (8, 3))]
     # streaming kernel (variant 3): strip widths, ring depths, rows per item (5 and 16 put item boundaries inside the domain)
-    combos += [(3, ti, jb, st) for ti in (32, 64, 128) for jb, st in ((0, 2), (5, 3), (16, 4))]
+    combos += [(3, ti, jb, st) for ti in (32, 64, 96, 128) for jb, st in ((0, 2), (5, 3), (16, 4))]
     for variant, ti, rows, stages in combos:
         for name, v in (("fv_variant", variant), ("fv_ti", ti), ("fv_rows", rows if variant == 2 else 0),
                         ("fv_jb", rows if variant == 3 else 0), ("fv_stages", stages)):
