@@ -1,4 +1,5 @@
-// K5 (variant 2, TMA-pipelined): fv_tp2d as a persistent, warp-specialised sm_100a kernel.
+// K5 (variant 2, TMA tiles): fv_tp2d as a persistent, warp-specialised sm_100a kernel.  Default only for launches
+// below ~12 M points since k_fv_stream.cu (variant 3) took over; kept bit-identical to it.
 // Spec: oracle/numpy_oracle.py fv_tp2d (no source in /root/reference).
 //
 // Design (DESIGN.md "K5"):
