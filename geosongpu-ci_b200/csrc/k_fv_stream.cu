@@ -244,11 +244,14 @@ int launch_stream(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j1
   FvStreamParams<T> P;
   P.nk = nk, P.i0 = i0, P.i1 = i1, P.j0 = j0, P.j1 = j1;
   P.nstrips = (i1 - i0 + TI - 1) / TI;
-  // Rows per item and grid size.  Items are long (a whole column height where possible: the six warm-up rows of
-  // an item are overhead -- C384x72 fp64: 453 us with 384-row items, 477 with 128, 519 with 64) and the persistent
-  // grid hands them out statically, so the split must come out even: for 1 .. 16 row blocks per column, model the
-  // busiest SM (waves of items per CTA x CTAs on that SM) and keep the best of  items / (SMs x that)  x  JB / (JB + 6).
-  // (fp32 C384x72 with one block: 1296 items on 888 CTAs = 1.46 per CTA, 267 us; two blocks: 248 us.)
+  // Rows per item and grid size.  Items are long (a whole column height where possible) and the persistent grid
+  // hands them out statically, so the split must come out even: for 1 .. 16 row blocks per column, model the
+  // busiest SM (waves of items per CTA x CTAs on that SM) and keep the best of
+  //     items / (SMs x that)  x  JB / (JB + 42).
+  // The 42 is measured, not derived: an item costs its six warm-up rows plus what fits the sweeps as ~36 more
+  // (C384x72 fp64: 453 us with 384-row items, 477 with 128, 519 with 64; C720x137 fp32: 1.87 ms with 720-row items,
+  // 2.00 with 360, 2.08 with 240), while balance decides when there are few waves (fp32 C384x72, 888 CTAs: one
+  // block per column = 1.46 items per CTA, 271 us; two blocks 254 us; three 279 us).
   // b2s_set_option("fv_jb", n) overrides the choice.
   const int h = j1 - j0;
   const int64_t max_ctas = (int64_t)sm_count() * ctas_per_sm;
@@ -261,7 +264,7 @@ int launch_stream(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j1
       const int64_t n = (int64_t)P.nstrips * ((h + cand - 1) / cand) * nk * nb;
       const int64_t waves = (n + max_ctas - 1) / max_ctas, g = even_grid(n);
       const int64_t busiest = (g + sm_count() - 1) / sm_count() * waves;
-      const double score = (double)n / ((double)sm_count() * busiest) * cand / (cand + 6.0);
+      const double score = (double)n / ((double)sm_count() * busiest) * cand / (cand + 42.0);
       if (score > best) best = score, jb = cand;
     }
   }
