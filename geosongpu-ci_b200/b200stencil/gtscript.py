@@ -9,6 +9,7 @@ hand-written sm_100a kernel (registry.py).
 from __future__ import annotations
 
 PARALLEL, FORWARD, BACKWARD = "PARALLEL", "FORWARD", "BACKWARD"
+THIS_K = "THIS_K"  # level index of the point (gt4py >= 1.0.4 experimental builtin; older stacks pass a k-index field)
 I, J, K = "I", "J", "K"
 IJ, IK, JK, IJK = "IJ", "IK", "JK", "IJK"
 

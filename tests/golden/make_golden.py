@@ -3,21 +3,8 @@
 gt4py / NDSL are not installable in this image, so the three pattern files cannot be executed as they are.
 What can be done is to take their stencil definitions verbatim -- this script reads
 `/root/reference/dsl_patterns/*.py`, pulls the `stencil` function and the `@function` helpers out of the
-file's AST -- and run them through a small interpreter of the gtscript subset they use, with the semantics
-of gt4py's numpy backend:
-
-  * `with computation(PARALLEL), interval(a, b)`: every statement is applied to the whole k-interval (right-hand
-    side evaluated for every point first, then stored) before the next statement starts;
-  * `with computation(FORWARD | BACKWARD), interval(a, b)`: k sequential, all statements of the block per level,
-    each statement over the whole horizontal plane (evaluate, then store);
-  * `interval(a, b)` is a Python slice of the k axis (negative = from the end, None = end), `interval(...)` = all;
-  * a 2-D (IJ) field broadcasts over k on reads and is written at (i, j);
-  * `field[di, dj, dk]` is a relative read; `dk` may be a run-time expression (variable-K offset), unchecked in
-    gt4py -- here an out-of-range read raises, so no fixture depends on undefined behaviour;
-  * `if` inside a computation masks the statements of its body per point;
-  * a `@function` is inlined: its parameters alias the caller's fields, its locals are per-point scalars, `while`
-    loops run per point;
-  * the value stored into a field is cast to the field's dtype (an integer `lev` becomes a float).
+file's AST -- and run them through `gtscript_interp.py` (beside this file), a small interpreter of the gtscript
+subset they use with the semantics of gt4py's numpy backend (listed in its docstring).
 
 The interpreter loops over points in pure Python: small cases only.  The outputs, together with the seeded
 inputs that produced them, are committed as `patterns_golden.npz`; `tests/test_golden_fixtures.py` checks the
@@ -31,7 +18,6 @@ the reference, and says so in its `note` entry.
 """
 from __future__ import annotations
 
-import ast
 import os
 import sys
 
@@ -42,186 +28,8 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 REFERENCE = "/root/reference/dsl_patterns"
 
 
-# ----------------------------------------------------------------------------------------------------------
-# gtscript-subset interpreter
-# ----------------------------------------------------------------------------------------------------------
-class UndefinedRead(IndexError):
-    pass
-
-
-class _Return(Exception):
-    def __init__(self, value):
-        self.value = value
-
-
-class GtscriptProgram:
-    """A stencil definition and the @function helpers of one pattern file, taken from its source text."""
-
-    def __init__(self, path: str, stencil_name: str = "stencil"):
-        with open(path) as f:
-            self.source = f.read()
-        tree = ast.parse(self.source)
-        self.functions = {}
-        self.stencil = None
-        for node in tree.body:
-            if isinstance(node, ast.FunctionDef):
-                decos = {d.id if isinstance(d, ast.Name) else getattr(d, "attr", "") for d in node.decorator_list}
-                if node.name == stencil_name:
-                    self.stencil = node
-                elif "function" in decos:
-                    self.functions[node.name] = node
-        if self.stencil is None:
-            raise ValueError(f"{path}: no `{stencil_name}` definition")
-        self.params = [a.arg for a in self.stencil.args.args]
-
-    # -- execution -----------------------------------------------------------------------------------------
-    def __call__(self, *arrays: np.ndarray) -> None:
-        if len(arrays) != len(self.params):
-            raise TypeError(f"stencil takes {self.params}, got {len(arrays)} arrays")
-        fields = dict(zip(self.params, arrays))
-        dom = next(a.shape for a in arrays if a.ndim == 3)
-        for a in arrays:
-            assert a.shape == dom or a.shape == dom[:2], (a.shape, dom)
-        self.dom = dom
-        for block in self.stencil.body:
-            if isinstance(block, ast.Expr) and isinstance(block.value, ast.Constant):
-                continue  # docstring
-            if not isinstance(block, ast.With):
-                raise NotImplementedError(ast.dump(block))
-            order, (k0, k1) = self._with_items(block)
-            ks = list(range(k0, k1))
-            if order == "PARALLEL":
-                for stmt in block.body:
-                    self._apply(stmt, fields, ks, mask=None)
-            else:
-                for k in (ks if order == "FORWARD" else ks[::-1]):
-                    for stmt in block.body:
-                        self._apply(stmt, fields, [k], mask=None)
-
-    def _with_items(self, block: ast.With):
-        order, interval = None, None
-        for item in block.items:
-            call = item.context_expr
-            assert isinstance(call, ast.Call) and isinstance(call.func, ast.Name), ast.dump(call)
-            if call.func.id == "computation":
-                order = call.args[0].id
-            elif call.func.id == "interval":
-                nk = self.dom[2]
-                if len(call.args) == 1 and isinstance(call.args[0], ast.Constant) and call.args[0].value is Ellipsis:
-                    interval = (0, nk)
-                else:
-                    a, b = (ast.literal_eval(x) for x in call.args)
-                    interval = tuple(range(nk)[slice(a, b)][i] for i in (0, -1))
-                    interval = (interval[0], interval[1] + 1)
-        assert order in ("PARALLEL", "FORWARD", "BACKWARD") and interval is not None
-        return order, interval
-
-    def _points(self, ks, mask):
-        ni, nj, _ = self.dom
-        for k in ks:
-            for i in range(ni):
-                for j in range(nj):
-                    if mask is None or mask[(i, j, k)]:
-                        yield i, j, k
-
-    def _apply(self, stmt, fields, ks, mask):
-        """One statement over the horizontal plane x the k-set: evaluate everywhere, then store."""
-        if isinstance(stmt, ast.If):
-            cond = {p: bool(self._eval(stmt.test, fields, {}, *p)) for p in self._points(ks, mask)}
-            full = {p: False for p in self._points(ks, None)}
-            for s in stmt.body:
-                self._apply(s, fields, ks, {**full, **cond})
-            if stmt.orelse:
-                neg = {p: not c for p, c in cond.items()}
-                for s in stmt.orelse:
-                    self._apply(s, fields, ks, {**full, **neg})
-            return
-        if isinstance(stmt, ast.Assign):
-            assert len(stmt.targets) == 1 and isinstance(stmt.targets[0], ast.Name), ast.dump(stmt)
-            target = fields[stmt.targets[0].id]
-            values = {p: self._eval(stmt.value, fields, {}, *p) for p in self._points(ks, mask)}
-            for (i, j, k), v in values.items():
-                if target.ndim == 3:
-                    target[i, j, k] = v  # NumPy casts to the field's dtype, as gt4py does
-                else:
-                    target[i, j] = v
-            return
-        raise NotImplementedError(ast.dump(stmt))
-
-    # -- expressions ---------------------------------------------------------------------------------------
-    def _read(self, arr, i, j, k):
-        ni, nj, nk = self.dom
-        if not (0 <= i < ni and 0 <= j < nj and 0 <= k < nk):
-            raise UndefinedRead(f"read at ({i},{j},{k}) outside the {self.dom} domain: undefined in gt4py")
-        return arr[i, j, k] if arr.ndim == 3 else arr[i, j]
-
-    def _eval(self, node, fields, local, i, j, k):
-        ev = lambda n: self._eval(n, fields, local, i, j, k)  # noqa: E731
-        if isinstance(node, ast.Constant):
-            return node.value
-        if isinstance(node, ast.Name):
-            if node.id in local:
-                return local[node.id]
-            return self._read(fields[node.id], i, j, k)
-        if isinstance(node, ast.Subscript):
-            arr = fields[node.value.id]
-            offs = node.slice.elts if isinstance(node.slice, ast.Tuple) else [node.slice]
-            di, dj, dk = (int(ev(o)) for o in offs)
-            return self._read(arr, i + di, j + dj, k + dk)
-        if isinstance(node, ast.UnaryOp):
-            v = ev(node.operand)
-            return {ast.USub: lambda: -v, ast.UAdd: lambda: +v, ast.Not: lambda: not v}[type(node.op)]()
-        if isinstance(node, ast.BinOp):
-            a, b = ev(node.left), ev(node.right)
-            return {ast.Add: lambda: a + b, ast.Sub: lambda: a - b, ast.Mult: lambda: a * b, ast.Div: lambda: a / b,
-                    ast.Pow: lambda: a ** b}[type(node.op)]()  # fmt: skip
-        if isinstance(node, ast.BoolOp):
-            vals = [ev(v) for v in node.values]
-            return all(vals) if isinstance(node.op, ast.And) else any(vals)
-        if isinstance(node, ast.Compare):
-            left = ev(node.left)
-            for op, right in zip(node.ops, node.comparators):
-                r = ev(right)
-                ok = {ast.Lt: left < r, ast.LtE: left <= r, ast.Gt: left > r, ast.GtE: left >= r, ast.Eq: left == r,
-                      ast.NotEq: left != r}[type(op)]  # fmt: skip
-                if not ok:
-                    return False
-                left = r
-            return True
-        if isinstance(node, ast.Call) and isinstance(node.func, ast.Name) and node.func.id in self.functions:
-            fn = self.functions[node.func.id]
-            # field arguments alias the caller's fields (gt4py inlines the function)
-            inner = dict(fields)
-            for p, a in zip(fn.args.args, node.args):
-                assert isinstance(a, ast.Name) and a.id in fields, "only field arguments are used by the patterns"
-                inner[p.arg] = fields[a.id]
-            try:
-                self._run_body(fn.body, inner, {}, i, j, k)
-            except _Return as r:
-                return r.value
-            raise ValueError(f"{fn.name} returned nothing")
-        raise NotImplementedError(ast.dump(node))
-
-    def _run_body(self, body, fields, local, i, j, k):
-        for s in body:
-            if isinstance(s, ast.Expr) and isinstance(s.value, ast.Constant):
-                continue
-            if isinstance(s, ast.Assign):
-                local[s.targets[0].id] = self._eval(s.value, fields, local, i, j, k)
-            elif isinstance(s, ast.AugAssign):
-                cur = local[s.target.id]
-                inc = self._eval(s.value, fields, local, i, j, k)
-                local[s.target.id] = {ast.Add: cur + inc, ast.Sub: cur - inc, ast.Mult: cur * inc}[type(s.op)]
-            elif isinstance(s, ast.While):
-                while self._eval(s.test, fields, local, i, j, k):
-                    self._run_body(s.body, fields, local, i, j, k)
-            elif isinstance(s, ast.If):
-                self._run_body(s.body if self._eval(s.test, fields, local, i, j, k) else s.orelse, fields, local, i, j, k)
-            elif isinstance(s, ast.Return):
-                raise _Return(self._eval(s.value, fields, local, i, j, k))
-            else:
-                raise NotImplementedError(ast.dump(s))
-
+sys.path.insert(0, HERE)
+from gtscript_interp import GtscriptProgram  # noqa: E402
 
 # ----------------------------------------------------------------------------------------------------------
 # fixtures
@@ -242,9 +50,9 @@ def _column_input(rng, shape, dtype):
 
 
 def pattern_fixtures() -> dict:
-    top = GtscriptProgram(os.path.join(REFERENCE, "Do__get_top_of_the_column.py"))
-    whl = GtscriptProgram(os.path.join(REFERENCE, "Do__while_in_gt_functions.py"))
-    hyb = GtscriptProgram(os.path.join(REFERENCE, "WIP__hybrid_index_2dout.py"))
+    top = GtscriptProgram.from_file(os.path.join(REFERENCE, "Do__get_top_of_the_column.py"))
+    whl = GtscriptProgram.from_file(os.path.join(REFERENCE, "Do__while_in_gt_functions.py"))
+    hyb = GtscriptProgram.from_file(os.path.join(REFERENCE, "WIP__hybrid_index_2dout.py"))
     assert top.params == ["PLEmb", "PLEmb_top", "out_field"]
     assert whl.params == ["in_field", "out_field"] and "while_in_function" in whl.functions
     assert hyb.params == ["data_field", "k_mask", "k_index_desired", "out_field"]
