@@ -164,10 +164,11 @@ def main(argv=None) -> int:
                     help="fv (default, the contract line): fv_tp2d transport step on C384x72; chain: BASELINE configs[4], "
                          "fv_tp2d + pe_prefix + remap on C720x137 (a separate report, see run_chain)")
     ap.add_argument("--no-overlap", action="store_true", help="exchange, then compute (no interior/frame split)")
-    ap.add_argument("--halo", choices=["auto", "p2p", "nccl"], default="auto",
+    ap.add_argument("--halo", choices=["auto", "p2p", "p2p-fused", "nccl"], default="auto",
                     help="multi-GPU halo exchange: p2p = device barrier + one peer-memory pull kernel over NVLink "
                          "(torch symmetric memory); nccl = packed strips + grouped NCCL send/recv overlapped with the "
-                         "interior; auto = p2p when it can be set up, else nccl")
+                         "interior; auto = p2p when it can be set up, else nccl; p2p-fused = EXPERIMENTAL one-launch "
+                         "handshake + pull (halo_pull_sync), not part of the default path")
     ap.add_argument("--graph", action="store_true", help="replay the step from a CUDA graph (default when --gpus > 1)")
     ap.add_argument("--no-graph", action="store_true", help="always launch eagerly")
     ap.add_argument("--fused-remap", action="store_true", help="[chain] fold pe_prefix into the remap kernel (remap_delp)")
@@ -217,21 +218,22 @@ def main(argv=None) -> int:
     g.manual_seed(20240724 + 4 + 1000 * rank)
     mk = lambda s, lo, hi: fields.empty(s, dtype, dev, batch=nsub).uniform_(lo, hi, generator=g)  # noqa: E731
     exchange, sym_q = "nccl", None
-    if world > 1 and ns.halo in ("auto", "p2p"):
+    if world > 1 and ns.halo in ("auto", "p2p", "p2p-fused"):
         try:
             from b200stencil.halo.p2p import SymmetricField
 
             sym_q = SymmetricField((ni + 6, nj + 6, NK), nsub, dtype, dev)
             exchange = "p2p"
         except Exception as exc:
-            if ns.halo == "p2p":
+            if ns.halo in ("p2p", "p2p-fused"):
                 raise
             sys.stderr.write(f"[bench] symmetric memory unavailable ({exc!r}); using the NCCL exchange\n")
     if sym_q is not None:
         q = sym_q.field.uniform_(0.5, 1.5, generator=g)
     else:
         q = mk((ni + 6, nj + 6, NK), 0.5, 1.5)
-    tr = FvTransport(part, n_gpus, rank, overlap=not ns.no_overlap, exchange=exchange, symmetric_q=sym_q)
+    tr = FvTransport(part, n_gpus, rank, overlap=not ns.no_overlap, exchange=exchange, symmetric_q=sym_q,
+                     fused_signal=ns.halo == "p2p-fused")
     crx, cry = mk((ni + 1, nj, NK), -0.9, 0.9), mk((ni, nj + 1, NK), -0.9, 0.9)
     xfx = mk((ni + 1, nj, NK), 0.9, 1.1).mul_(crx)
     yfx = mk((ni, nj + 1, NK), 0.9, 1.1).mul_(cry)
@@ -448,6 +450,7 @@ def main(argv=None) -> int:
                 "launch": "cuda-graph replay of the whole step" if graph is not None else "eager launches",
                 "l2": f"inputs larger than L2: {input_mb:.0f} MB of inputs per GPU per step vs 126 MB L2, no flush needed",
                 "halo_exchange": ("none (all neighbours on this GPU: one local halo_move kernel)" if n_gpus == 1 else
+                                  "p2p-fused (experimental): one halo_pull_sync kernel, handshake inside" if tr.p2p is not None and tr.p2p.fused_signal else
                                   "p2p: device barrier + one halo_pull kernel over NVLink peer memory" if tr.p2p is not None else
                                   "nccl: pack kernel + grouped NCCL send/recv + unpack kernel"),
                 "halo_bytes_over_nvlink_per_gpu_per_step": (tr.p2p.remote_bytes if tr.p2p is not None

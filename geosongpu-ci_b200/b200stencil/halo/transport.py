@@ -39,7 +39,7 @@ class FvTransport:
     the :class:`~b200stencil.halo.p2p.SymmetricField` given as ``symmetric_q``)."""
 
     def __init__(self, part: CubedSpherePartitioner, n_gpus: int, gpu: int, process_group=None,
-                 overlap: bool = True, side: int = 32, exchange: str = "nccl", symmetric_q=None):
+                 overlap: bool = True, side: int = 32, exchange: str = "nccl", symmetric_q=None, fused_signal: bool = False):
         self.part, self.n_gpus, self.gpu = part, n_gpus, gpu
         self.exchange = exchange
         self.updater = HaloUpdater(part, n_gpus, gpu, process_group=process_group)
@@ -49,7 +49,7 @@ class FvTransport:
 
             if symmetric_q is None:
                 raise ValueError('exchange="p2p" needs the SymmetricField that holds q')
-            self.p2p = P2PHaloUpdater(part, n_gpus, gpu, symmetric_q)
+            self.p2p = P2PHaloUpdater(part, n_gpus, gpu, symmetric_q, fused_signal=fused_signal)  # fused: EXPERIMENTAL
             overlap = False
         self.overlap = overlap and bool(self.updater.plan.peers)
         self.interior, self.frame = split_regions(part.nx, part.ny, part.halo, side)

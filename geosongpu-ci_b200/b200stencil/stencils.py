@@ -179,6 +179,16 @@ def prepare_halo_move(links, nk: int, src, dst, max_strip: int) -> "_abi.Prepare
     )  # fmt: skip
 
 
+def prepare_halo_pull_sync(links, nk: int, dst, max_strip: int, my_rank: int, world: int, peer_flags, sync_state) -> "_abi.PreparedCall":
+    """EXPERIMENTAL one-launch halo update: neighbour handshake + pull (csrc/k_halo.cu halo_pull_sync); links int64
+    [nlinks, 12], peer_flags int64 [world] (addresses of every rank's int32 flag array), sync_state int32 [3]."""
+    return _abi.prepare(
+        "halo_pull_sync", _abi.precision_of(dst),
+        dict(nlinks=int(links.shape[0]), nk=int(nk), max_strip=int(max_strip), my_rank=int(my_rank), world=int(world),
+             links=links, peer_flags=peer_flags, sync_state=sync_state, dst=dst),
+    )  # fmt: skip
+
+
 def prepare_halo_pull(links, nk: int, dst, max_strip: int) -> "_abi.PreparedCall":
     """One-kernel halo update over peer memory (csrc/k_halo.cu halo_pull); links int64 [nlinks, 11]."""
     return _abi.prepare(

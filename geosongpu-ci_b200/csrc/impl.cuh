@@ -53,6 +53,9 @@ int halo_move(int nlinks, int nk, int max_strip, const int64_t* links, const T* 
 
 template <typename T>
 int halo_pull(int nlinks, int nk, int max_strip, const int64_t* links, T* dst, cudaStream_t s);
+template <typename T>
+int halo_pull_sync(int nlinks, int nk, int max_strip, int my_rank, int world, const int64_t* links,
+                   const int64_t* peer_flags, int* sync_state, T* dst, cudaStream_t s);
 
 }  // namespace impl
 }  // namespace b2s

@@ -76,6 +76,25 @@ def main():
     dist.barrier()
     if rank == 0:
         print(f"multigpu_check ok on {world} GPUs: peer-memory halo_pull adjacency + p2p step == NCCL step", flush=True)
+
+    # ---- EXPERIMENTAL one-launch handshake + pull (halo_pull_sync): only with B2S_CHECK_FUSED=1.  Three updates in a
+    #      row exercise the device-resident epoch; every wait in the kernel is bounded (status word), so a protocol
+    #      error shows up as an exception here, not as a hung GPU.
+    if os.environ.get("B2S_CHECK_FUSED") == "1":
+        fused = P2PHaloUpdater(part, world, rank, sf, fused_signal=True)
+        for rep in range(3):
+            for b in range(nsub):
+                sf.field[b].copy_(torch.from_numpy(global_id_field(part, rank * nsub + b, nk)))
+            torch.cuda.synchronize()
+            dist.barrier()
+            fused.update()
+            torch.cuda.synchronize()
+            fused.check()
+            check_field(part, world, rank, sf.field, nk)
+            dist.barrier()
+        assert int(fused.sync_state[0].item()) == 3 and int(fused.sync_state[1].item()) == 0
+        if rank == 0:
+            print(f"multigpu_check ok on {world} GPUs: fused handshake + pull (halo_pull_sync), 3 epochs", flush=True)
     sys.stdout.flush()
     os._exit(0)
 

@@ -196,3 +196,35 @@ def test_halo_exchange_gloo(world):
     import torch.multiprocessing as mp
 
     mp.spawn(_gloo_worker, args=(world, _free_port(), 12, 2), nprocs=world, join=True)
+
+
+def test_pull_tables_name_the_owner_of_every_strip():
+    """halo/p2p.py build_pull_table: the 12-word table of the (experimental) one-launch exchange is the 11-word table
+    plus the rank that owns each source strip; -1 marks strips of sub-domains on the same GPU (nothing to wait for)."""
+    import torch
+
+    from b200stencil import fields
+    from b200stencil.halo import p2p
+    from b200stencil.halo.updater import FieldGeometry
+
+    for n_gpus in (2, 4, 8):
+        part = CubedSpherePartitioner(24, layout_for(n_gpus), 3)
+        nsub = part.subdomains_per_gpu(n_gpus)
+        f = fields.empty((part.nx + 6, part.ny + 6, 5), torch.float64, "cpu", batch=nsub)
+        geo = FieldGeometry(f, 3)
+        ptrs = [1000 * (r + 1) for r in range(n_gpus)]
+        neighbours = {}
+        for gpu in range(n_gpus):
+            t11, b11 = p2p.build_pull_table(part, n_gpus, gpu, geo, 8, ptrs, list(range(n_gpus)))
+            t12, b12 = p2p.build_pull_table(part, n_gpus, gpu, geo, 8, ptrs, list(range(n_gpus)), with_source_rank=True)
+            assert t11.shape[1] == p2p.PULL_WORDS and t12.shape[1] == p2p.PULL_SYNC_WORDS
+            assert np.array_equal(t11, t12[:, :11]) and b11 == b12
+            assert len(t12) >= 4 * nsub  # at least one strip per edge of every sub-domain
+            for row in t12:
+                owner = int(row[11])
+                assert row[10] == ptrs[gpu if owner < 0 else owner] and owner != gpu
+            neighbours[gpu] = {int(r) for r in t12[:, 11] if r >= 0}
+        # the handshake relies on adjacency being symmetric: whoever I wait for also waits for me
+        for a, ns_ in neighbours.items():
+            for b in ns_:
+                assert a in neighbours[b]
