@@ -1,0 +1,111 @@
+"""Model check of the neighbour handshake of halo_pull_sync (csrc/k_halo.cu, experimental one-launch exchange).
+
+The kernel cannot be run on several GPUs in this container, but its PROTOCOL can be executed: every rank is a
+sequence of micro-operations, a random scheduler interleaves the ranks, and the invariants a ping-pong time loop
+needs are asserted on every read and write:
+
+  step n of rank r:   announce   flags[p][r] = n for every neighbour p        (st.release.sys in block (0,0,0))
+                      pull       for every link: wait flags[r][p] >= n, then read p's field      (ld.acquire.sys)
+                      compute    write field version n into the OTHER buffer                      (the stencil)
+
+  * a pull at step n must see exactly version n-1 of the neighbour's field, in the buffer that holds it;
+  * nobody may be overwriting a buffer while a neighbour still has to read it;
+  * no deadlock: the scheduler always finds a runnable rank until every rank has finished.
+
+The same model with the wait removed must FAIL, or the check would prove nothing."""
+import random
+
+import pytest
+
+from b200stencil.halo.partitioner import CubedSpherePartitioner, layout_for
+
+
+def gpu_neighbours(n_gpus):
+    part = CubedSpherePartitioner(24, layout_for(n_gpus), 3)
+    nb = {g: set() for g in range(n_gpus)}
+    for l in part.all_links():
+        a, b = part.gpu_of(l.src, n_gpus), part.gpu_of(l.dst, n_gpus)
+        if a != b:
+            nb[b].add(a)  # b pulls from a
+    return nb
+
+
+class Violation(AssertionError):
+    pass
+
+
+def run_schedule(nb, steps, rng, wait=True):
+    world = len(nb)
+    flags = [[0] * world for _ in range(world)]           # flags[r][p]: latest epoch announced by p to r
+    version = [[0, -1] for _ in range(world)]             # version[r][buf]: field version held by each ping-pong buffer
+    writing = [None] * world                              # buffer a rank is overwriting right now
+    # per-rank program counter: (step, phase, pending links)
+    pc = [{"n": 1, "phase": "announce", "todo": None} for _ in range(world)]
+    done = 0
+    guard = 0
+    while done < world:
+        guard += 1
+        assert guard < 200000, "scheduler did not terminate"
+        runnable = []
+        for r in range(world):
+            st = pc[r]
+            if st["n"] > steps:
+                continue
+            if st["phase"] == "pull" and wait:
+                if any(flags[r][p] >= st["n"] for p in st["todo"]):
+                    runnable.append(r)
+            else:
+                runnable.append(r)
+        if not runnable:
+            raise Violation("deadlock: every unfinished rank is waiting")
+        r = rng.choice(runnable)
+        st = pc[r]
+        n = st["n"]
+        if st["phase"] == "announce":
+            for p in nb[r]:
+                flags[p][r] = n
+            st["phase"], st["todo"] = "pull", sorted(nb[r])
+        elif st["phase"] == "pull":
+            ready = [p for p in st["todo"] if flags[r][p] >= n] if wait else list(st["todo"])
+            p = rng.choice(ready)
+            src_buf = (n - 1) % 2                        # version n-1 lives in buffer (n-1) % 2
+            if writing[p] == src_buf:
+                raise Violation(f"rank {r} step {n}: reads buffer {src_buf} of rank {p} while {p} overwrites it")
+            if version[p][src_buf] != n - 1:
+                raise Violation(f"rank {r} step {n}: expected version {n - 1} of rank {p}, found {version[p][src_buf]}")
+            st["todo"].remove(p)
+            if not st["todo"]:
+                st["phase"] = "compute_begin"
+        elif st["phase"] == "compute_begin":
+            writing[r] = n % 2
+            version[r][n % 2] = None                     # being overwritten: neither the old nor the new version
+            st["phase"] = "compute_end"
+        else:  # compute_end
+            version[r][n % 2] = n
+            writing[r] = None
+            st["n"], st["phase"] = n + 1, "announce"
+            if st["n"] > steps:
+                done += 1
+    return True
+
+
+@pytest.mark.parametrize("n_gpus", [2, 4, 8])
+def test_handshake_orders_pulls_and_overwrites(n_gpus):
+    nb = gpu_neighbours(n_gpus)
+    for g, s in nb.items():  # the protocol needs symmetric adjacency: whoever I wait for also waits for me
+        assert s and all(g in nb[p] for p in s)
+    rng = random.Random(20240724 + n_gpus)
+    for _ in range(300):
+        assert run_schedule(nb, steps=5, rng=rng)
+
+
+def test_without_the_wait_the_model_catches_the_race():
+    nb = gpu_neighbours(4)
+    rng = random.Random(1)
+    caught = 0
+    for _ in range(200):
+        try:
+            run_schedule(nb, steps=5, rng=rng, wait=False)
+        except Violation:
+            caught += 1
+    assert caught > 150
