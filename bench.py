@@ -7,8 +7,9 @@
 Workload (BASELINE.json configs[3], the configuration the headline target is quoted on):
 FV3-style horizontal finite-volume flux/advection stencil (fv_tp2d, 3-cell halo) on the C384 cubed
 sphere (6 tiles x 384 x 384 columns) x 72 levels, synthetic fields.  One STEP = halo update of q from
-the neighbouring sub-domains (same-GPU copies at N = 1, + NCCL exchange over NVLink at N > 1) followed
-by fv_tp2d on every sub-domain the GPU hosts.  The domain is fixed, so scaling is STRONG.
+the neighbouring sub-domains (ONE kernel: same-GPU copies, and at N > 1 a neighbour handshake + pull over NVLink
+peer memory, overlapped with the cells of the stencil that read no halo) followed by fv_tp2d on every sub-domain the
+GPU hosts.  The domain is fixed, so scaling is STRONG.
 
 Prints ONE JSON line (rank 0).  Keys follow the driver contract; see DESIGN.md "Measurement".
 """
@@ -41,6 +42,14 @@ def algorithmic_bytes_per_point(es: int) -> float:
 # ---------------------------------------------------------------------------------------------------
 
 
+def host_cores() -> int:
+    """Cores this process may run on (the affinity mask, not os.cpu_count(): a cgroup / taskset can be narrower)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_sample_inputs(ni, nj, nk, dtype, seed=20240728):
     import numpy as np
 
@@ -63,34 +72,66 @@ def cpu_sample_inputs(ni, nj, nk, dtype, seed=20240728):
     return q, crx, xfx, cry, yfx, rarea, out
 
 
+class CpuStep:
+    """The GPU arm's step on the host cores: halo fill of q on all six tiles (oracle/c halo_move over the same link
+    table) followed by oracle/c fv_tp2d on each of the six 384 x 384 x 72 tiles -- the whole C384x72 workload."""
+
+    def __init__(self, dtype_name: str):
+        import numpy as np
+        import torch
+
+        from b200stencil.halo.partitioner import CubedSpherePartitioner
+        from b200stencil.halo.updater import FieldGeometry, HaloPlan
+        from oracle.c_oracle import COracle
+
+        self.dtype = np.float64 if dtype_name == "f64" else np.float32
+        try:
+            self.orc = COracle(native=True)  # -O3 -march=native, built on this machine
+            self.build = "gcc -O3 -march=native -fopenmp"
+        except Exception:
+            self.orc = COracle(native=False)
+            self.build = "gcc -O2 -fopenmp (portable build)"
+        # all the host threads this process may use, whatever OMP_NUM_THREADS says (torchrun exports 1)
+        self.cores = host_cores()
+        self.orc.set_threads(self.cores)
+        self.threads = self.orc.threads
+        if self.cores > 1 and self.threads <= 1:
+            raise RuntimeError(f"CPU baseline would run on 1 of {self.cores} cores: refusing to time it")
+        n = CUBE_N
+        self.tiles = [cpu_sample_inputs(n, n, NK, self.dtype, seed=20240728 + t) for t in range(1)]
+        # six tiles: q is one batch storage (the halo fill crosses tiles); the other inputs are tile 0's, reused --
+        # their values do not change the work and generating 2.5 GB of random numbers would dominate the leg
+        self.q = np.empty((6, NK, n + 6, n + 6), dtype=self.dtype)
+        for t in range(6):
+            self.q[t] = self.tiles[0][0].transpose(2, 1, 0)
+        self.q_view = [self.q[t].transpose(2, 1, 0) for t in range(6)]  # [i, j, k], i-fastest
+        self.outs = [self.tiles[0][6]] + [np.zeros_like(self.tiles[0][6]) for _ in range(1)]
+        part = CubedSpherePartitioner(n, (1, 1), HALO)
+        tq = torch.from_numpy(self.q).permute(0, 3, 2, 1)
+        self.links = HaloPlan(part, 1, 0).tables(FieldGeometry(tq, HALO))["local"]
+        self.points = 6 * n * n * NK
+
+    def __call__(self):
+        flat = self.q.reshape(-1)
+        self.orc.halo_move(self.links, NK, flat, flat)
+        _, crx, xfx, cry, yfx, rarea, _ = self.tiles[0]
+        for t in range(6):
+            self.orc.fv_tp2d(self.q_view[t], crx, xfx, cry, yfx, rarea, self.outs[t & 1])
+
+
 def time_cpu_port(dtype_name: str, budget_s: float = 20.0, steps=None, warmup: int = 1):
-    """Time the C/OpenMP restatement (oracle/c) on ONE tile of the workload (384 x 384 x 72), all host threads.
+    """Time the C/OpenMP restatement (oracle/c) on the WHOLE workload step (halo fill + six tiles), all host threads.
 
-    Returns (points_per_second, description dict).  The sample is 1/6 of a step of the real workload.
-    """
-    import numpy as np
-
-    from oracle.c_oracle import COracle
-
-    dtype = np.float64 if dtype_name == "f64" else np.float32
-    try:
-        orc = COracle(native=True)  # -O3 -march=native, built on this machine
-        build = "gcc -O3 -march=native -fopenmp"
-    except Exception:
-        orc = COracle(native=False)
-        build = "gcc -O2 -fopenmp (portable build)"
-    threads = orc.threads
-    ni = nj = CUBE_N
-    args = cpu_sample_inputs(ni, nj, NK, dtype)
-    pts = ni * nj * NK
+    Returns (points_per_second, description dict, per-step times)."""
+    step = CpuStep(dtype_name)
     for _ in range(warmup):
-        orc.fv_tp2d(*args)
+        step()
     times = []
     t_begin = time.perf_counter()
     n = 0
     while True:
         t0 = time.perf_counter()
-        orc.fv_tp2d(*args)
+        step()
         times.append(time.perf_counter() - t0)
         n += 1
         if steps is not None:
@@ -101,12 +142,12 @@ def time_cpu_port(dtype_name: str, budget_s: float = 20.0, steps=None, warmup: i
     best = min(times)
     med = statistics.median(times)
     info = {
-        "value": pts / med, "unit": UNIT, "cores": threads, "kind": "port",
-        "sample": f"oracle/c fv_tp2d ({build}) on 1 of the 6 tiles (384x384x{NK}, {dtype_name}), "
-                  f"{n} runs, median {med * 1e3:.1f} ms, best {best * 1e3:.1f} ms",
+        "value": step.points / med, "unit": UNIT, "cores": step.threads, "kind": "port",
+        "sample": f"oracle/c halo_move + fv_tp2d ({step.build}, {step.threads} OpenMP threads of {step.cores} usable cores) on the whole "
+                  f"step: halo fill + 6 tiles of 384x384x{NK} ({dtype_name}), {n} steps, median {med * 1e3:.1f} ms, best {best * 1e3:.1f} ms",
         "ms_per_sample": med * 1e3,
     }  # fmt: skip
-    return pts / med, info, times
+    return step.points / med, info, times
 
 
 def time_numpy_port(dtype_name: str):
@@ -128,18 +169,20 @@ def time_numpy_port(dtype_name: str):
 
 def run_reference(ns) -> int:
     """--impl reference: the reference's CPU implementation of the path.  gt4py/NDSL cannot be installed
-    here, so this is the oracle port (C/OpenMP, every host thread) on the same config/metric."""
+    here, so this is the oracle port (C/OpenMP, every host thread) on the same config/metric:
+    one step = halo fill + fv_tp2d on all six tiles, like the GPU arm's."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    value, info, times = time_cpu_port(ns.dtype, steps=max(1, ns.steps), warmup=max(1, ns.warmup))
+    value, info, times = time_cpu_port(ns.dtype, steps=max(1, min(ns.steps, 30)), warmup=max(1, min(ns.warmup, 3)))
     ms = statistics.median(times) * 1e3
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ns.gpus, "steps": len(times),
-        "warmup": max(1, ns.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+        "warmup": max(1, min(ns.warmup, 3)), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": ns.dtype, "data": "synthetic",
-        "config": {"workload": "fv_tp2d C384x72 (CPU port; each step = 1 of the 6 tiles, 384x384x72)",
-                   "grid": f"C{CUBE_N}", "levels": NK, "halo": HALO},
+        "config": {"workload": "fv_tp2d C384x72 (CPU port): halo fill of q + PPM flux-form update on all 6 tiles, the GPU arm's step",
+                   "grid": f"C{CUBE_N}", "tiles": 6, "levels": NK, "halo": HALO, "same_config": True,
+                   "steps_note": "at most 30 timed steps (bounded CPU leg)"},
         "cpu_baseline": {k: info[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -160,17 +203,18 @@ def main(argv=None) -> int:
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--dtype", choices=["f64", "f32"], default="f64")
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
-    ap.add_argument("--workload", choices=["fv", "chain"], default="fv",
+    ap.add_argument("--workload", choices=["fv", "chain", "patterns"], default="fv",
                     help="fv (default, the contract line): fv_tp2d transport step on C384x72; chain: BASELINE configs[4], "
-                         "fv_tp2d + pe_prefix + remap on C720x137 (a separate report, see run_chain)")
-    ap.add_argument("--no-overlap", action="store_true", help="exchange, then compute (no interior/frame split)")
-    ap.add_argument("--halo", choices=["auto", "p2p", "p2p-fused", "nccl"], default="auto",
-                    help="multi-GPU halo exchange: p2p = device barrier + one peer-memory pull kernel over NVLink "
-                         "(torch symmetric memory); nccl = packed strips + grouped NCCL send/recv overlapped with the "
-                         "interior; auto = p2p when it can be set up, else nccl; p2p-fused = EXPERIMENTAL one-launch "
-                         "handshake + pull (halo_pull_sync), not part of the default path")
-    ap.add_argument("--graph", action="store_true", help="replay the step from a CUDA graph (default when --gpus > 1)")
-    ap.add_argument("--no-graph", action="store_true", help="always launch eagerly")
+                         "fv_tp2d + pe_prefix + remap on C720x137; patterns: BASELINE configs[1], the dsl_patterns column "
+                         "stencils on C96x72 (separate reports, see run_chain / run_patterns)")
+    ap.add_argument("--no-overlap", action="store_true", help="exchange, then compute (no halo-independent-cells-first overlap)")
+    ap.add_argument("--overlap", action="store_true", help="force the overlapped (gated) step also at N = 1")
+    ap.add_argument("--halo", choices=["auto", "device", "nccl"], default="auto",
+                    help="halo exchange: device (= auto) the library-owned exchange, ONE kernel per update (neighbour handshake "
+                         "+ pull over NVLink peer memory, b2s_halo_*), forked next to a gated stencil launch; nccl = the "
+                         "portable baseline: packed strips + grouped NCCL send/recv overlapped with an interior launch")
+    ap.add_argument("--no-graph", action="store_true", help="launch eagerly (default: the step is replayed from a CUDA graph at every N)")
+    ap.add_argument("--regions", type=int, default=0, help="timed regions of K steps each (median reported); 0 = auto")
     ap.add_argument("--fused-remap", action="store_true", help="[chain] fold pe_prefix into the remap kernel (remap_delp)")
     ap.add_argument("--hws-dump", default=None, help="write the hws sampler record of the run (npz) to this path")
     ap.add_argument("--e2e-steps", type=int, default=3)
@@ -181,13 +225,16 @@ def main(argv=None) -> int:
         return run_reference(ns)
     if ns.workload == "chain":
         return run_chain(ns)
+    if ns.workload == "patterns":
+        return run_patterns(ns)
 
     import torch
     import torch.distributed as dist
 
     from b200stencil import _abi, fields, hostio, stencils
     from b200stencil.bench import harness
-    from b200stencil.halo.partitioner import CubedSpherePartitioner, layout_for
+    from b200stencil.halo.device import HaloContext
+    from b200stencil.halo.partitioner import CubedSpherePartitioner, expected_halo, global_id_field, layout_for
     from b200stencil.halo.transport import FvTransport
     from b200stencil.hws import Sampler
 
@@ -203,8 +250,11 @@ def main(argv=None) -> int:
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = hostio.bind_to_gpu_numa_node(local_rank) if world > 1 else None  # before any pinned allocation
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # torch.distributed: timing plumbing (barrier, max over ranks), the session-name bootstrap and the NCCL
+        # baseline exchange; the product exchange is libb200stencil's
         dist.init_process_group("nccl", device_id=dev)
     dtype = torch.float64 if ns.dtype == "f64" else torch.float32
     es = 8 if ns.dtype == "f64" else 4
@@ -213,27 +263,53 @@ def main(argv=None) -> int:
     nsub = part.subdomains_per_gpu(n_gpus)
     ni, nj = part.nx, part.ny
 
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
     # synthetic fields, resident in HBM before the timed region (SURVEY.md 8d recipe, device RNG)
     g = torch.Generator(device=dev)
     g.manual_seed(20240724 + 4 + 1000 * rank)
     mk = lambda s, lo, hi: fields.empty(s, dtype, dev, batch=nsub).uniform_(lo, hi, generator=g)  # noqa: E731
-    exchange, sym_q = "nccl", None
-    if world > 1 and ns.halo in ("auto", "p2p", "p2p-fused"):
-        try:
-            from b200stencil.halo.p2p import SymmetricField
+    use_device = ns.halo in ("auto", "device")
+    ctx = HaloContext(rank, world, local_rank)
+    overlap = (not ns.no_overlap) and (world > 1 or ns.overlap)
 
-            sym_q = SymmetricField((ni + 6, nj + 6, NK), nsub, dtype, dev)
-            exchange = "p2p"
-        except Exception as exc:
-            if ns.halo in ("p2p", "p2p-fused"):
-                raise
-            sys.stderr.write(f"[bench] symmetric memory unavailable ({exc!r}); using the NCCL exchange\n")
-    if sym_q is not None:
-        q = sym_q.field.uniform_(0.5, 1.5, generator=g)
+    # ---- halo_check: the exchange the timed loop uses, on a global-id field, every halo cell against geometry ----
+    halo_check = None
+    if use_device:
+        nk_chk = 2
+        idf = ctx.field((ni + 6, nj + 6, nk_chk), nsub, torch.float64)
+        for b in range(nsub):
+            idf[b].copy_(torch.from_numpy(global_id_field(part, rank * nsub + b, nk_chk)))
+        barrier()
+        ex_chk = ctx.plan(idf, part)
+        for _ in range(2):
+            ex_chk.update()
+        torch.cuda.synchronize()
+        bad = 0
+        for b in range(nsub):
+            want = torch.from_numpy(expected_halo(part, rank * nsub + b, nk_chk)).to(dev)
+            bad += int((idf[b] != want).sum().item())
+        epoch, status = ctx.status()
+        flag = torch.tensor([bad + status], device=dev, dtype=torch.int64)
+        if world > 1:
+            dist.all_reduce(flag)
+        if int(flag.item()) != 0:
+            raise SystemExit(f"[bench] halo_check FAILED on rank {rank}: {bad} wrong halo cells, device status {status}")
+        halo_check = "ok"
+        barrier()
+
+    if use_device:
+        q = ctx.field((ni + 6, nj + 6, NK), nsub, dtype)
+        q.uniform_(0.5, 1.5, generator=g)
+        ex = ctx.plan(q, part)
+        tr = FvTransport(part, n_gpus, rank, exchange="device", halo_exchange=ex, overlap=overlap)
     else:
         q = mk((ni + 6, nj + 6, NK), 0.5, 1.5)
-    tr = FvTransport(part, n_gpus, rank, overlap=not ns.no_overlap, exchange=exchange, symmetric_q=sym_q,
-                     fused_signal=ns.halo == "p2p-fused")
+        ex = None
+        tr = FvTransport(part, n_gpus, rank, overlap=not ns.no_overlap, exchange="nccl")
     crx, cry = mk((ni + 1, nj, NK), -0.9, 0.9), mk((ni, nj + 1, NK), -0.9, 0.9)
     xfx = mk((ni + 1, nj, NK), 0.9, 1.1).mul_(crx)
     yfx = mk((ni, nj + 1, NK), 0.9, 1.1).mul_(cry)
@@ -243,25 +319,41 @@ def main(argv=None) -> int:
     total_points = 6 * CUBE_N * CUBE_N * NK
     local_points = nsub * ni * nj * NK
     input_mb = sum(t.numel() * es for t in args[:6]) / 1e6
+    barrier()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
+    # ---- the product step against the NCCL baseline step (same fields): bit-identical, or the run stops ----
+    nccl_equal = None
+    if use_device and world > 1:
+        tr.step(*args)
+        q_b = fields.empty((ni + 6, nj + 6, NK), dtype, dev, batch=nsub)
+        q_b.copy_(q)
+        q_b[:, :3, 3:-3] = -1.0
+        q_b[:, -3:, 3:-3] = -1.0  # scrub west / east halos: the NCCL exchange has to refill them
+        out_b = fields.empty((ni, nj, NK), dtype, dev, batch=nsub)
+        FvTransport(part, n_gpus, rank, overlap=False, exchange="nccl").step(q_b, crx, xfx, cry, yfx, rarea, out_b)
         torch.cuda.synchronize()
+        same = torch.equal(out_b, q_out) and torch.equal(q_b[:, :, 3:-3], q[:, :, 3:-3]) and torch.equal(q_b[:, 3:-3], q[:, 3:-3])
+        flag = torch.tensor([0 if same else 1], device=dev, dtype=torch.int64)
+        dist.all_reduce(flag)
+        if int(flag.item()) != 0:
+            raise SystemExit(f"[bench] rank {rank}: the device-exchange step differs from the NCCL baseline step")
+        nccl_equal = True
+        del q_b, out_b
+        barrier()
 
     # ---- warm-up ----
     for _ in range(max(3, ns.warmup)):
         tr.step(*args)
     barrier()
+    if ex is not None:
+        ctx.check()
 
-    full_call, interior_call, frame_calls = tr.calls(*args)
-    dominant = interior_call if tr.overlap else full_call
+    full_call = tr.calls(*args)[0]
 
-    # Multi-GPU steps are a handful of ~50 us kernels plus an NCCL group: the whole step (both streams,
-    # NCCL included) is captured ONCE into a CUDA graph and replayed, so the host never paces the device.
-    use_graph = (n_gpus > 1 and not ns.no_graph) or ns.graph
+    # The whole step (both streams, exchange included) is captured ONCE into a CUDA graph and replayed at every N
+    # (N = 1 included: one launch mode for the whole scaling curve), so the host never paces the device.
     graph = None
-    if use_graph:
+    if not ns.no_graph:
         try:
             cap = torch.cuda.Stream(device=dev)
             cap.wait_stream(torch.cuda.current_stream(dev))
@@ -276,8 +368,9 @@ def main(argv=None) -> int:
             graph = None
             barrier()
 
-    # ---- timed region: K steps between two CUDA events on the launching stream, barrier + sync on
-    #      both sides; eager mode also brackets the dominant fv_tp2d launch of every step ----
+    # ---- timed regions: K steps between two CUDA events on the launching stream, barrier + sync on both sides.
+    #      The K-step region is repeated and the MEDIAN region reported (a 20-step region is ~10 ms at N = 1 and
+    #      ~1.5 ms at N = 8: one region is at the mercy of a single clock excursion) ----
     sampler = None
     if rank == 0:
         try:
@@ -285,71 +378,57 @@ def main(argv=None) -> int:
         except Exception:
             sampler = None
     K = ns.steps
-    # the dominant launch is bracketed on (up to) 200 steps spread evenly over the timed region, so a clock
-    # that sags under the power cap late in a long loop is seen by the kernel time as it is by the step time
-    k_stride = max(1, K // 200)
-    k_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-                for _ in range(len(range(0, K, k_stride)))]
-
-    def eager_step_with_events(ev):
-        """tr.step() with two events around the dominant launch (same kernels, same order)."""
-        if tr.p2p is not None:
-            tr.p2p.update()
-            ev[0].record()
-            full_call()
-            ev[1].record()
-        elif tr.overlap:
-            tr.updater.start(q)
-            ev[0].record()
-            interior_call()
-            ev[1].record()
-            tr.updater.wait()
-            for c in frame_calls:
-                c()
-        else:
-            tr.updater.update(q)
-            ev[0].record()
-            full_call()
-            ev[1].record()
-
+    regions = ns.regions if ns.regions > 0 else 5
     launches0 = _abi.launch_count()
     t_wall0 = time.time()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    if graph is not None:
-        for _ in range(K):
-            graph.replay()
-    else:
-        for it in range(K):
-            if it % k_stride == 0:
-                eager_step_with_events(k_events[it // k_stride])
-            else:
+    region_ms = []
+    for _ in range(regions):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        if graph is not None:
+            for _ in range(K):
+                graph.replay()
+        else:
+            for _ in range(K):
                 tr.step(*args)
-    e1.record()
-    barrier()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        region_ms.append(ms)
     t_wall1 = time.time()
-    if tr.p2p is not None:
-        launches_per_step = 2  # halo_pull + fv_tp2d (the barrier kernel is torch's, not counted)
+    if ex is not None:
+        ctx.check()  # no device-side wait timed out during the timed regions
+    if ex is not None:
+        launches_per_step = 2  # k_halo_exchange + fv_tp2d (gated or plain)
     else:
-        launches_per_step = (1 if not tr.updater.plan.peers else 3) + (1 if not tr.overlap else 1 + len(frame_calls))
-    launches = K * launches_per_step if graph is not None else _abi.launch_count() - launches0
-    elapsed_ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
+        launches_per_step = (1 if not tr.updater.plan.peers else 3) + (1 if not tr.overlap else 1 + len(tr.frame))
+    launches = regions * K * launches_per_step if graph is not None else _abi.launch_count() - launches0
+    elapsed_ms = statistics.median(region_ms)
     ms_per_step = elapsed_ms / K
     value = total_points * K / (elapsed_ms * 1e-3)
-    if graph is not None:
-        # a replayed graph leaves no place for events: the dominant launch is timed in an eager pass of the
-        # same step loop right after the timed region (CUDA events on its stream, not under a profiler)
-        for ev in k_events[:60]:
-            eager_step_with_events(ev)
-        barrier()
-        kernel_ms = statistics.median(a.elapsed_time(b) for a, b in k_events[:60])
-    else:
-        kernel_ms = statistics.median(a.elapsed_time(b) for a, b in k_events)
+
+    # ---- the dominant launch (fv_tp2d on the GPU's whole batch), timed in an eager pass of exchange-then-stencil
+    #      steps right after the timed regions: CUDA events on its stream, not under a profiler ----
+    k_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(60)]
+    halo_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(60)]
+    for hv, ev in zip(halo_events, k_events):
+        hv[0].record()
+        if ex is not None:
+            ex.update()
+        else:
+            tr.updater.update(q)
+        hv[1].record()
+        ev[0].record()
+        full_call()
+        ev[1].record()
+    barrier()
+    kernel_ms = statistics.median(a.elapsed_time(b) for a, b in k_events)
+    halo_ms = statistics.median(a.elapsed_time(b) for a, b in halo_events)
     hws_summary = None
     if sampler is not None:
         time.sleep(0.05)
@@ -377,18 +456,14 @@ def main(argv=None) -> int:
 
     # ---- roofline of the dominant kernel ----
     peaks = harness.measured_peaks(ROOT)
-    if tr.overlap:
-        r = tr.interior
-        kernel_points = nsub * (r[1] - r[0]) * (r[3] - r[2]) * NK
-        kernel_name = "k_fv_stream (interior rectangle launch)"
-    else:
-        kernel_points = local_points
-        kernel_name = "k_fv_stream (full-domain launch)"
+    kernel_points = local_points
+    small = kernel_points < 12000000
+    kernel_name = ("k_fv_tma" if small else "k_fv_stream") + " (fv_tp2d on the GPU's whole batch of sub-domains)"
     kbytes = kernel_points * algorithmic_bytes_per_point(es)
     achieved = kbytes / (kernel_ms * 1e-3) / 1e9
     traffic = None
     prof = os.path.join(ROOT, "profiles", "fv_stream_traffic.json")  # ncu --set full capture of the same launch
-    if os.path.exists(prof) and not tr.overlap and n_gpus == 1:  # the capture is of the N = 1 launch (6 x 384 x 384 x 72)
+    if os.path.exists(prof) and n_gpus == 1:  # the capture is of the N = 1 launch (6 x 384 x 384 x 72)
         with open(prof) as f:
             traffic = json.load(f).get(ns.dtype, {}).get("dram_bytes_per_launch")
     roofline = {
@@ -396,23 +471,30 @@ def main(argv=None) -> int:
         "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": traffic, "kernel": kernel_name,
         "kernel_ms": round(kernel_ms, 4), "algorithmic_bytes_per_launch": kbytes, "peak_source": peaks["source"],
         "frac_of_nominal_8TBs": round(achieved / harness.NOMINAL_HBM_GBS, 4),
+        "timed": "CUDA events around the ungated launch in 60 eager exchange-then-stencil steps after the timed regions",
+        "halo_exchange_ms": round(halo_ms, 4),
+        "step_frac": round(total_points / n_gpus * algorithmic_bytes_per_point(es) / (ms_per_step * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
     }  # fmt: skip
 
-    # ---- e2e: same step through the host-buffer API (pinned host fields, H2D + D2H inside the timed region) ----
+    # ---- e2e: the same step through the host-buffer API (pinned host fields; H2D, halo update, stencil and D2H
+    #      inside the timed region) ----
     e2e = None
     if not ns.skip_e2e:
+        pcie = hostio.measure_pcie(dev)
         pipe = hostio.FvTp2dHost(ni, nj, NK, dtype, dev)
         host = pipe.host_fields(nsub)
         for name, t in zip(pipe.NAMES, args[:6]):
             host[name].copy_(t)  # the synthetic inputs, now living on the host
         torch.cuda.synchronize()
-        pipe(host)  # warm-up
+        hx = ex.update if ex is not None else (lambda: tr.updater.update(q))
+        hsync = ctx.barrier if world > 1 else None
+        pipe(host, q_dev=q, exchange=hx, sync=hsync)  # warm-up
         barrier()
         h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         h0.record()
         for _ in range(ns.e2e_steps):
-            pipe(host)
+            pipe(host, q_dev=q, exchange=hx, sync=hsync)
         h1.record()
         barrier()
         e2e_ms = max(h0.elapsed_time(h1), (time.perf_counter() - t0) * 1e3)  # pipe() returns host-synchronised
@@ -420,13 +502,21 @@ def main(argv=None) -> int:
             t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_ms = float(t.item())
-        # parity of the host path with the resident path on this rank's first sub-domain
-        ok = bool(torch.equal(host["q_out"][0].to(dev), _fv_reference_of(stencils, fields, args, dev)))
+        # parity of the host path with the resident path (same inputs, same halo update) on this rank
+        tr.step(*args)
+        torch.cuda.synchronize()
+        ok = bool(torch.equal(host["q_out"].to(dev), q_out))
+        step_s = e2e_ms * 1e-3 / ns.e2e_steps
         e2e = {
             "value": total_points * ns.e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
             "h2d_bytes_per_step": pipe.h2d_bytes * world, "d2h_bytes_per_step": pipe.d2h_bytes * world,
             "ms_per_step": e2e_ms / ns.e2e_steps, "steps": ns.e2e_steps, "matches_resident_path": ok,
-            "api": "b200stencil.hostio.FvTp2dHost (pinned host fields, 3-stream upload|compute|download pipeline)",
+            "includes_halo_update": True,
+            "api": "b200stencil.hostio.FvTp2dHost (pinned host fields; q uploaded, halo update, then a 3-stream upload|compute|download pipeline over the sub-domains)",
+            "pcie_gbs": pcie,
+            # the step moves h2d + d2h bytes per GPU over a full-duplex link: its floor is the longer of the two directions
+            "frac_of_pcie": round(max(pipe.h2d_bytes / (pcie["h2d"] * 1e9), pipe.d2h_bytes / (pcie["d2h"] * 1e9)) / step_s, 4),
+            "numa_node": numa,
         }  # fmt: skip
         del pipe, host
 
@@ -434,7 +524,7 @@ def main(argv=None) -> int:
     cpu = None
     cpu_numpy = None
     if rank == 0 and n_gpus == 1 and not ns.skip_cpu:
-        _, cpu, _ = time_cpu_port(ns.dtype, budget_s=15.0)
+        _, cpu, _ = time_cpu_port(ns.dtype, budget_s=12.0)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
         cpu_numpy = time_numpy_port(ns.dtype)
 
@@ -446,28 +536,32 @@ def main(argv=None) -> int:
             "config": {
                 "workload": "fv_tp2d transport step on C384x72 (BASELINE configs[3]): halo update of q + PPM flux-form update",
                 "grid": f"C{CUBE_N}", "tiles": 6, "levels": NK, "halo": HALO, "layout": list(layout_for(n_gpus)),
-                "subdomains_per_gpu": nsub, "subdomain": [ni, nj], "overlap_exchange": tr.overlap,
+                "subdomains_per_gpu": nsub, "subdomain": [ni, nj], "overlap_exchange": bool(tr.overlap),
                 "launch": "cuda-graph replay of the whole step" if graph is not None else "eager launches",
                 "l2": f"inputs larger than L2: {input_mb:.0f} MB of inputs per GPU per step vs 126 MB L2, no flush needed",
-                "halo_exchange": ("none (all neighbours on this GPU: one local halo_move kernel)" if n_gpus == 1 else
-                                  "p2p-fused (experimental): one halo_pull_sync kernel, handshake inside" if tr.p2p is not None and tr.p2p.fused_signal else
-                                  "p2p: device barrier + one halo_pull kernel over NVLink peer memory" if tr.p2p is not None else
-                                  "nccl: pack kernel + grouped NCCL send/recv + unpack kernel"),
-                "halo_bytes_over_nvlink_per_gpu_per_step": (tr.p2p.remote_bytes if tr.p2p is not None
-                                                            else tr.updater.bytes_sent_per_update),
+                "halo_exchange": ("device: one k_halo_exchange launch (neighbour handshake + pull over NVLink peer memory, b2s_halo_*)"
+                                  + (", forked beside one gated fv_tp2d launch (halo-independent cells first)" if tr.overlap else ", then fv_tp2d")
+                                  if ex is not None else
+                                  "nccl baseline: pack kernel + grouped NCCL send/recv + unpack kernel" if n_gpus > 1 else
+                                  "local halo_move kernel"),
+                "halo_bytes_over_nvlink_per_gpu_per_step": (ex.remote_bytes if ex is not None else tr.updater.bytes_sent_per_update),
+                "timed_regions": regions, "region_ms": [round(x, 4) for x in region_ms], "reported": "median region",
             },
+            "halo_check": halo_check, "device_step_equals_nccl_step": nccl_equal,
             "roofline": roofline, "clocks": clocks, "hws": hws_summary, "gpu_launches": int(launches),
             "e2e": e2e, "cpu_baseline": cpu,
         }  # fmt: skip
         if cpu_numpy is not None:
             line["cpu_baseline_numpy"] = cpu_numpy
         print(json.dumps(line), flush=True)
+    graph = None
+    torch.cuda.synchronize()
     if world > 1:
-        # A CUDA graph that holds NCCL kernels must die before the communicator, or the destroy blocks:
-        # drop it, drain the device, and leave without the (hang-prone) communicator teardown.
-        graph = None
-        torch.cuda.synchronize()
         dist.barrier()
+    ctx.finalize()
+    if world > 1:
+        # A CUDA graph that held NCCL kernels must die before the communicator, or the destroy blocks:
+        # the graph is gone, the device drained; leave without the (hang-prone) communicator teardown.
         sys.stdout.flush()
         sys.stderr.flush()
         os._exit(0)
@@ -503,15 +597,13 @@ def run_chain(ns) -> int:
     g = torch.Generator(device=dev)
     g.manual_seed(20240724 + 5 + 1000 * rank)
     mk = lambda s, lo, hi: fields.empty(s, dtype, dev, batch=nsub).uniform_(lo, hi, generator=g)  # noqa: E731
-    exchange, sym_q = "nccl", None
-    if world > 1:
-        from b200stencil.halo.p2p import SymmetricField
+    from b200stencil.halo.device import HaloContext
 
-        sym_q = SymmetricField((ni + 6, nj + 6, nk), nsub, dtype, dev)
-        exchange = "p2p"
-        q = sym_q.field.uniform_(0.5, 1.5, generator=g)
-    else:
-        q = mk((ni + 6, nj + 6, nk), 0.5, 1.5)
+    ctx = HaloContext(rank, world, local_rank)
+    exchange = "device"
+    q = ctx.field((ni + 6, nj + 6, nk), nsub, dtype)
+    q.uniform_(0.5, 1.5, generator=g)
+    ex = ctx.plan(q, part)
     crx, cry = mk((ni + 1, nj, nk), -0.9, 0.9), mk((ni, nj + 1, nk), -0.9, 0.9)
     xfx = mk((ni + 1, nj, nk), 0.9, 1.1).mul_(crx)
     yfx = mk((ni, nj + 1, nk), 0.9, 1.1).mul_(cry)
@@ -525,7 +617,7 @@ def run_chain(ns) -> int:
     pe2[..., -1] = pe1[..., -1]
     q_adv = fields.empty((ni, nj, nk), dtype, dev, batch=nsub)
     q_new = fields.empty((ni, nj, nk), dtype, dev, batch=nsub)
-    chain = DycoreChain(FvTransport(part, world, rank, overlap=False, exchange=exchange, symmetric_q=sym_q),
+    chain = DycoreChain(FvTransport(part, world, rank, overlap=world > 1 and not ns.no_overlap, exchange=exchange, halo_exchange=ex),
                         fused=ns.fused_remap)
     args = (q, crx, xfx, cry, yfx, rarea, delp, pe2, q_adv, pe1, q_new)
 
@@ -538,7 +630,7 @@ def run_chain(ns) -> int:
         chain.step(*args)
     barrier()
     graph = None
-    if world > 1 and not ns.no_graph:
+    if not ns.no_graph:
         cap = torch.cuda.Stream(device=dev)
         cap.wait_stream(torch.cuda.current_stream(dev))
         graph = torch.cuda.CUDAGraph()
@@ -570,31 +662,57 @@ def run_chain(ns) -> int:
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": ns.dtype,
             "data": "synthetic",
             "config": {"workload": "dycore chain on C720x137 (BASELINE configs[4])", "subdomains_per_gpu": nsub,
-                       "subdomain": [ni, nj], "halo_exchange": exchange if world > 1 else "local",
+                       "subdomain": [ni, nj], "halo_exchange": "device (k_halo_exchange, b2s_halo_*)",
+                       "overlap_exchange": world > 1 and not ns.no_overlap,
                        "launch": "cuda-graph replay" if graph is not None else "eager launches",
                        "vertical": "remap_delp (pe_prefix fused into remap)" if ns.fused_remap else "pe_prefix + remap"},
             "roofline": {"bound": "hbm", "achieved": round(gbs, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": round(gbs / peaks["hbm_gbs"], 4), "traffic": None,
                          "kernel": "whole chain (unfused algorithmic bytes 96.1 B/pt in fp64), per GPU"},
         }), flush=True)  # fmt: skip
+    graph = None
+    torch.cuda.synchronize()
+    ctx.check()
     if world > 1:
-        graph = None
-        torch.cuda.synchronize()
         dist.barrier()
+    ctx.finalize()
+    if world > 1:
         sys.stdout.flush()
         os._exit(0)
     return 0
 
 
-def _fv_reference_of(stencils, fields, args, dev):
-    """fv_tp2d of sub-domain 0 recomputed on resident fields WITHOUT a halo update (what the host path computes)."""
+def run_patterns(ns) -> int:
+    """BASELINE configs[1]: the dsl_patterns column stencils at their own size, C96 (6 tiles) x 72 levels, fp64 and fp32.
+
+    Not the contract line.  Each stencil is timed as CUDA-graph replays over rotating buffer sets (32 MB fields are
+    smaller than L2: the sets rotate so that the working set is > 2.5x L2), CUDA events around the replays; one JSON
+    line with a roofline entry per stencil (algorithmic bytes of SURVEY.md 8d)."""
     import torch
 
-    q, crx, xfx, cry, yfx, rarea, q_out = args
-    out = fields.empty(tuple(q_out.shape[1:]), q_out.dtype, dev)
-    stencils.fv_tp2d(q[0], crx[0], xfx[0], cry[0], yfx[0], rarea[0], out)
-    torch.cuda.synchronize()
-    return out
+    from b200stencil.bench import harness, sweep
+
+    torch.cuda.set_device(0)
+    rows = []
+    for stencil in ("top_of_column", "while_in_function", "hybrid_index_2dout"):
+        for dt in (torch.float64, torch.float32):
+            rows.append(sweep.run_one(stencil, "C96x72", dt, iters=max(5, min(ns.steps, 30)), warmup=max(3, min(ns.warmup, 10)), graph=True))
+    peaks = harness.measured_peaks(ROOT)
+    pts = sum(r["points"] for r in rows)
+    ms = sum(r["median_ms"] for r in rows)
+    worst = min(rows, key=lambda r: r["frac_measured_peak"])
+    print(json.dumps({
+        "metric": "grid-cells x levels per second, dsl_patterns column stencils (C96x72, 6 tiles), fp64 + fp32",
+        "value": pts / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": max(5, min(ns.steps, 30)), "warmup": max(3, min(ns.warmup, 10)),
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+f32", "data": "synthetic",
+        "config": {"workload": "dsl_patterns S1 top_of_column, S2 while_in_function, S3 hybrid_index_2dout on C96x72 (BASELINE configs[1])",
+                   "launch": "cuda-graph replay, rotating buffer sets (working set > 2.5x L2)", "step": "one launch of each stencil in each precision"},
+        "roofline": {"bound": "hbm", "achieved": worst["GBps"], "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": worst["frac_measured_peak"],
+                     "traffic": None, "kernel": f"{worst['stencil']} {worst['dtype']} (the lowest of the six)"},
+        "stencils": {f"{r['stencil']}_{r['dtype']}": {"median_us": round(r["median_ms"] * 1e3, 2), "GBps": r["GBps"], "frac": r["frac_measured_peak"],
+                                                      "frac_of_nominal_8TBs": r["frac_nominal_8TBs"], "gpts_per_s": r["gpts_per_s"]} for r in rows},
+    }), flush=True)  # fmt: skip
+    return 0
 
 
 if __name__ == "__main__":

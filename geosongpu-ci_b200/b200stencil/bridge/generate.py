@@ -270,6 +270,21 @@ RUNTIME_SYMBOLS = [
     "b2s_set_option",
     "b2s_get_option",
     "b2s_launch_count",
+    "b2s_halo_init",
+    "b2s_halo_finalize",
+    "b2s_halo_rank",
+    "b2s_halo_world",
+    "b2s_halo_barrier",
+    "b2s_halo_alloc",
+    "b2s_halo_free",
+    "b2s_halo_peer_ptr",
+    "b2s_halo_plan",
+    "b2s_halo_plan_remote_bytes",
+    "b2s_halo_exchange",
+    "b2s_halo_exchange_start",
+    "b2s_halo_exchange_wait",
+    "b2s_halo_gate",
+    "b2s_halo_status",
 ]
 
 RUNTIME_CDEF = """
@@ -282,6 +297,21 @@ int b2s_sm_count(void);
 int b2s_set_option(const char* name, int value);
 int b2s_get_option(const char* name);
 int64_t b2s_launch_count(void);
+int b2s_halo_init(const char* session, int rank, int world, int device, int64_t* ctx);
+int b2s_halo_finalize(int64_t ctx);
+int b2s_halo_rank(int64_t ctx);
+int b2s_halo_world(int64_t ctx);
+int b2s_halo_barrier(int64_t ctx);
+int b2s_halo_alloc(int64_t ctx, int64_t nbytes, void** ptr);
+int b2s_halo_free(int64_t ctx, void* ptr);
+int b2s_halo_peer_ptr(int64_t ctx, const void* ptr, int peer, void** peer_ptr);
+int b2s_halo_plan(int64_t ctx, const void* field, int elem_size, int nk, int nlinks, const int64_t* links, int* plan);
+int64_t b2s_halo_plan_remote_bytes(int64_t ctx, int plan);
+int b2s_halo_exchange(int64_t ctx, int plan, void* stream);
+int b2s_halo_exchange_start(int64_t ctx, int plan, int gated, void* stream);
+int b2s_halo_exchange_wait(int64_t ctx, void* stream);
+int b2s_halo_gate(int64_t ctx, int** gate);
+int b2s_halo_status(int64_t ctx, int* epoch, int* status);
 """
 
 HEADER_PROLOGUE = """/* b200stencil.h -- C-ABI of libb200stencil.so (GENERATED, do not edit).
@@ -335,6 +365,59 @@ B2S_API int b2s_set_option(const char* name, int value);
 B2S_API int b2s_get_option(const char* name);
 /* number of kernels this library has launched in this process (bench.py gpu_launches) */
 B2S_API int64_t b2s_launch_count(void);
+
+/* ---- multi-GPU halo exchange lifecycle (csrc/halo_ctx.cu) -------------------------------------------------------
+ * The reference passes the communicator THROUGH the C boundary (argument type MPI: py_ftn_interface/argument.py:54-86,
+ * MPI_Comm_f2c in base.py:78-96) and brackets the run with init / finalize (example_def_dycore.yaml:4,21,71); the halo
+ * update itself is NDSL's HaloUpdater over mpi4py.  Here the exchange is owned by the library: one rank (process or
+ * thread) per GPU of ONE node, peer memory over NVLink, no MPI, no NCCL, no Python.
+ *   session   the analogue of the communicator: a name shared by the ranks of one run (POSIX shared-memory rendezvous;
+ *             choose it unique per run, e.g. from the launcher's job id).  May be NULL when world == 1.
+ *   ctx       opaque handle (int64 so that Fortran can hold it in an integer(c_int64_t)).
+ * Collective calls (every rank, same order): b2s_halo_init, b2s_halo_alloc, b2s_halo_free, b2s_halo_barrier,
+ * b2s_halo_finalize, and every exchange.  Host-side waits are bounded (B2S_RDV_TIMEOUT seconds, default 60). */
+B2S_API int b2s_halo_init(const char* session, int rank, int world, int device, int64_t* ctx);
+B2S_API int b2s_halo_finalize(int64_t ctx);
+B2S_API int b2s_halo_rank(int64_t ctx);
+B2S_API int b2s_halo_world(int64_t ctx);
+B2S_API int b2s_halo_barrier(int64_t ctx);
+/* symmetric device allocation: the same nbytes on every rank, every peer's buffer mapped into this process */
+B2S_API int b2s_halo_alloc(int64_t ctx, int64_t nbytes, void** ptr);
+B2S_API int b2s_halo_free(int64_t ctx, void* ptr);
+/* address, in this process, of rank `peer`'s copy of the byte `ptr` points to (ptr inside a b2s_halo_alloc buffer) */
+B2S_API int b2s_halo_peer_ptr(int64_t ctx, const void* ptr, int peer, void** peer_ptr);
+/* bind a link table to a field.  links: HOST int64[nlinks][12]; words 0..9 as for b2s_halo_move (element offsets
+ * relative to `field`, the same on every rank), [10] = rank that owns the source sub-domain, [11] = 0. */
+B2S_API int b2s_halo_plan(int64_t ctx, const void* field, int elem_size, int nk, int nlinks, const int64_t* links, int* plan);
+B2S_API int64_t b2s_halo_plan_remote_bytes(int64_t ctx, int plan);
+/* halo update = ONE kernel (neighbour handshake + pull over peer memory).  b2s_halo_exchange runs it on `stream`;
+ * _start forks it onto the context's own high-priority stream (ordered after the work already on `stream`), _wait
+ * joins: what the caller enqueues on `stream` in between overlaps the exchange.  Both can be captured in a CUDA graph.
+ * gated != 0: the kernel raises the gate when the halos are complete; exactly one gated stencil launch
+ * (b2s_fv_tp2d_gated_c) must consume it between _start and _wait. */
+B2S_API int b2s_halo_exchange(int64_t ctx, int plan, void* stream);
+B2S_API int b2s_halo_exchange_start(int64_t ctx, int plan, int gated, void* stream);
+B2S_API int b2s_halo_exchange_wait(int64_t ctx, void* stream);
+/* device address of the gate words (int32[4]) for gated stencil launches */
+B2S_API int b2s_halo_gate(int64_t ctx, int** gate);
+/* host-synchronising: exchanges completed; status bit 0 = a neighbour's announcement timed out on the device,
+ * bit 1 = a gated stencil gave up waiting for the gate */
+B2S_API int b2s_halo_status(int64_t ctx, int* epoch, int* status);
+int b2s_halo_init(const char* session, int rank, int world, int device, int64_t* ctx);
+int b2s_halo_finalize(int64_t ctx);
+int b2s_halo_rank(int64_t ctx);
+int b2s_halo_world(int64_t ctx);
+int b2s_halo_barrier(int64_t ctx);
+int b2s_halo_alloc(int64_t ctx, int64_t nbytes, void** ptr);
+int b2s_halo_free(int64_t ctx, void* ptr);
+int b2s_halo_peer_ptr(int64_t ctx, const void* ptr, int peer, void** peer_ptr);
+int b2s_halo_plan(int64_t ctx, const void* field, int elem_size, int nk, int nlinks, const int64_t* links, int* plan);
+int64_t b2s_halo_plan_remote_bytes(int64_t ctx, int plan);
+int b2s_halo_exchange(int64_t ctx, int plan, void* stream);
+int b2s_halo_exchange_start(int64_t ctx, int plan, int gated, void* stream);
+int b2s_halo_exchange_wait(int64_t ctx, void* stream);
+int b2s_halo_gate(int64_t ctx, int** gate);
+int b2s_halo_status(int64_t ctx, int* epoch, int* status);
 """
 
 HEADER_EPILOGUE = """#ifdef __cplusplus

@@ -39,6 +39,7 @@ SOURCES = {
     "k_remap_slab.cu": ["-fmad=false"],
     "k_remap_ppm.cu": [],
     "k_halo.cu": [],
+    "halo_ctx.cu": [],
 }
 
 

@@ -1,0 +1,198 @@
+"""Library-owned halo exchange over NVLink peer memory: the Python face of ``b2s_halo_*`` (csrc/halo_ctx.cu).
+
+Rendezvous, peer mapping, the neighbour handshake and the pull all live behind the C-ABI
+(include/b200stencil.h "multi-GPU halo exchange lifecycle"); this module only
+
+* picks a session name every rank agrees on (the analogue of the communicator the reference passes through its
+  bridge, /root/reference/src/tcn/py_ftn_interface/argument.py:54-86),
+* wraps the symmetric allocation in a torch tensor (device storage only),
+* turns the partitioner's links into the host table ``b2s_halo_plan`` wants.
+
+A halo update is ONE kernel (handshake + pull).  ``start()`` forks it onto the context's own stream so it overlaps
+whatever the caller launches before ``wait()``; with ``gated=True`` a gated stencil (``stencils.fv_tp2d_gated``)
+computes the cells that read no halo while the exchange is in flight and the rest once the gate opens.
+A C or Fortran caller drives the same entry points without Python (tests/c_abi/abi_driver.c).
+"""
+from __future__ import annotations
+
+import os
+import uuid
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from .. import _abi
+from .partitioner import CubedSpherePartitioner
+
+PLAN_WORDS = 12
+
+
+def make_session(group=None) -> str:
+    """A name unique to this run and equal on every rank.
+
+    With an initialised torch.distributed group (an optional bootstrap helper, nothing on the data path) rank 0
+    draws a uuid and broadcasts it; otherwise B2S_SESSION, else the launcher's rendezvous identity."""
+    try:
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized():
+            box = [uuid.uuid4().hex if dist.get_rank(group) == 0 else None]
+            dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            return f"{box[0]}"
+    except Exception:
+        pass
+    if os.environ.get("B2S_SESSION"):
+        return os.environ["B2S_SESSION"]
+    env = os.environ
+    return "_".join(str(env.get(k, "x")) for k in ("MASTER_ADDR", "MASTER_PORT", "TORCHELASTIC_RUN_ID", "TORCHELASTIC_RESTART_COUNT")).replace("/", "-")
+
+
+class _RawDeviceMemory:
+    """``__cuda_array_interface__`` holder for a library-owned allocation (torch keeps it alive with the tensor)."""
+
+    def __init__(self, ptr: int, nbytes: int, owner):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 3}
+        self._owner = owner
+
+
+def _padded(ni: int, dtype: torch.dtype) -> int:
+    per = 16 // torch.empty((), dtype=dtype).element_size()
+    return (ni + per - 1) // per * per
+
+
+class HaloContext:
+    """One rank of a halo-exchange session (``b2s_halo_init`` ... ``b2s_halo_finalize``)."""
+
+    def __init__(self, rank: int = 0, world: int = 1, device: Optional[int] = None, session: Optional[str] = None):
+        ffi, lib = _abi.load()
+        self._ffi, self._lib = ffi, lib
+        self.rank, self.world = int(rank), int(world)
+        self.device = int(device if device is not None else torch.cuda.current_device())
+        _abi.ensure_init(self.device)
+        if self.world > 1 and not session:
+            session = make_session()
+        out = ffi.new("int64_t*")
+        _abi.check("b2s_halo_init", lib.b2s_halo_init((session or "").encode(), self.rank, self.world, self.device, out))
+        self.handle = int(out[0])
+        self._gate = None
+
+    # ---- memory ---------------------------------------------------------------------------------
+    def alloc(self, nbytes: int) -> int:
+        """Collective symmetric allocation; returns this rank's device address."""
+        p = self._ffi.new("void**")
+        _abi.check("b2s_halo_alloc", self._lib.b2s_halo_alloc(self.handle, int(nbytes), p))
+        return int(self._ffi.cast("uintptr_t", p[0]))
+
+    def free(self, ptr: int) -> None:
+        _abi.check("b2s_halo_free", self._lib.b2s_halo_free(self.handle, self._ffi.cast("void*", int(ptr))))
+
+    def peer_ptr(self, ptr: int, peer: int) -> int:
+        p = self._ffi.new("void**")
+        _abi.check("b2s_halo_peer_ptr", self._lib.b2s_halo_peer_ptr(self.handle, self._ffi.cast("void*", int(ptr)), int(peer), p))
+        return int(self._ffi.cast("uintptr_t", p[0]))
+
+    def _tensor(self, ptr: int, nbytes: int, dtype: torch.dtype) -> torch.Tensor:
+        raw = torch.as_tensor(_RawDeviceMemory(ptr, nbytes, self), device=torch.device("cuda", self.device))
+        return raw.view(dtype)
+
+    def field(self, shape_ijk: Sequence[int], batch: int, dtype=torch.float64, fill: Optional[float] = 0.0) -> torch.Tensor:
+        """A batch field [b, i, j, k] (i-fastest, rows padded to 16 bytes) in symmetric memory (collective)."""
+        ni, nj, nk = (int(s) for s in shape_ijk)
+        nip = _padded(ni, dtype)
+        numel = int(batch) * nk * nj * nip
+        es = torch.empty((), dtype=dtype).element_size()
+        flat = self._tensor(self.alloc(numel * es), numel * es, dtype)
+        if fill is not None:
+            flat.fill_(fill)
+        return flat.view(int(batch), nk, nj, nip).permute(0, 3, 2, 1)[:, :ni]
+
+    # ---- exchange -------------------------------------------------------------------------------
+    @property
+    def gate(self) -> torch.Tensor:
+        """int32[4] device words the gated stencils poll (``b2s_halo_gate``)."""
+        if self._gate is None:
+            p = self._ffi.new("int**")
+            _abi.check("b2s_halo_gate", self._lib.b2s_halo_gate(self.handle, p))
+            self._gate = self._tensor(int(self._ffi.cast("uintptr_t", p[0])), 16, torch.int32)
+        return self._gate
+
+    def plan(self, field: torch.Tensor, part: CubedSpherePartitioner, n_gpus: Optional[int] = None, gpu: Optional[int] = None,
+             ranks: Optional[Sequence[int]] = None) -> "HaloExchange":
+        """Bind the links that fill this GPU's halos to ``field`` (a tensor returned by :meth:`field`).
+
+        ``ranks[g]`` = session rank that hosts GPU ``g`` of the decomposition (default: identity)."""
+        n_gpus = self.world if n_gpus is None else n_gpus
+        gpu = self.rank if gpu is None else gpu
+        ranks = list(ranks) if ranks is not None else list(range(n_gpus))
+        table = build_plan_table(part, n_gpus, gpu, field, ranks)
+        out = self._ffi.new("int*")
+        tbl = np.ascontiguousarray(table, dtype=np.int64)
+        _abi.check("b2s_halo_plan", self._lib.b2s_halo_plan(
+            self.handle, self._ffi.cast("void*", field.data_ptr()), field.element_size(), int(field.shape[3]), len(tbl),
+            self._ffi.cast("int64_t*", tbl.ctypes.data) if len(tbl) else self._ffi.NULL, out))  # fmt: skip
+        return HaloExchange(self, int(out[0]), field)
+
+    def barrier(self) -> None:
+        _abi.check("b2s_halo_barrier", self._lib.b2s_halo_barrier(self.handle))
+
+    def status(self):
+        """(exchanges completed, status bits); host-synchronising.  Status != 0: a device-side wait timed out."""
+        e, s = self._ffi.new("int*"), self._ffi.new("int*")
+        _abi.check("b2s_halo_status", self._lib.b2s_halo_status(self.handle, e, s))
+        return int(e[0]), int(s[0])
+
+    def check(self) -> None:
+        epoch, status = self.status()
+        if status:
+            raise RuntimeError(f"halo exchange: a device-side wait gave up (status {status}, epoch {epoch}): "
+                               "a neighbour did not announce its field or the gate never opened")  # fmt: skip
+
+    def finalize(self) -> None:
+        if self.handle:
+            h, self.handle = self.handle, 0
+            self._gate = None
+            _abi.check("b2s_halo_finalize", self._lib.b2s_halo_finalize(h))
+
+
+def build_plan_table(part: CubedSpherePartitioner, n_gpus: int, gpu: int, field: torch.Tensor, ranks: Sequence[int]) -> np.ndarray:
+    """int64 [nlinks, 12] host table of ``b2s_halo_plan``: element offsets relative to ``field``'s first element."""
+    from .updater import FieldGeometry
+
+    geo = FieldGeometry(field, part.halo)
+    rows = []
+    for l in part.all_links():  # every link whose destination is one of my sub-domains
+        if part.gpu_of(l.dst, n_gpus) != gpu:
+            continue
+        owner = part.gpu_of(l.src, n_gpus)
+        b_src, b_dst = part.local_index(l.src, n_gpus), part.local_index(l.dst, n_gpus)
+        rows.append([
+            geo.cell(b_src, l.si0, l.sj0), geo.step(l.sdi, l.sdj), geo.step(l.spi, l.spj), geo.sk,
+            geo.cell(b_dst, l.di0, l.dj0), geo.step(l.ddi, l.ddj), geo.step(l.dpi, l.dpj), geo.sk,
+            l.nd, l.np_, int(ranks[owner]), 0,
+        ])  # fmt: skip
+    return np.asarray(rows, dtype=np.int64).reshape(-1, PLAN_WORDS)
+
+
+class HaloExchange:
+    """A link table bound to one field: ``update()`` = exchange on the current stream; ``start()/wait()`` = forked."""
+
+    def __init__(self, ctx: HaloContext, plan: int, field: torch.Tensor):
+        self.ctx, self.plan, self.field = ctx, plan, field
+        self.remote_bytes = int(ctx._lib.b2s_halo_plan_remote_bytes(ctx.handle, plan))
+        self.bytes_sent_per_update = self.remote_bytes  # pulled, not sent: the same volume crosses NVLink
+
+    def _stream(self, stream):
+        if stream is None:
+            stream = torch.cuda.current_stream(self.field.device).cuda_stream
+        return self.ctx._ffi.cast("void*", int(stream))
+
+    def update(self, stream=None) -> None:
+        _abi.check("b2s_halo_exchange", self.ctx._lib.b2s_halo_exchange(self.ctx.handle, self.plan, self._stream(stream)))
+
+    def start(self, gated: bool = False, stream=None) -> None:
+        _abi.check("b2s_halo_exchange_start",
+                   self.ctx._lib.b2s_halo_exchange_start(self.ctx.handle, self.plan, 1 if gated else 0, self._stream(stream)))
+
+    def wait(self, stream=None) -> None:
+        _abi.check("b2s_halo_exchange_wait", self.ctx._lib.b2s_halo_exchange_wait(self.ctx.handle, self._stream(stream)))

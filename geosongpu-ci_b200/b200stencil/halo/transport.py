@@ -1,9 +1,10 @@
 """One flux-form transport step on a GPU's batch of sub-domains: halo update of q + fv_tp2d.
 
 This is the unit bench.py times (BASELINE config 4: "FV3-style horizontal finite-volume
-flux/advection stencil with 3-point halo on C384x72, halo exchange at 2/4/8 GPUs").  With more than
-one GPU the exchange runs on a communication stream while the interior rectangle -- whose stencil
-never reads a halo cell -- is computed; the boundary frame follows once the halos have landed.
+flux/advection stencil with 3-point halo on C384x72, halo exchange at 2/4/8 GPUs").  The exchange runs
+on its own stream while the cells whose stencil never reads a halo cell are computed; the cells along
+the edges follow once the halos have landed -- inside ONE gated stencil launch on the product path
+(library-owned exchange, halo/device.py), as an interior launch + frame launches on the NCCL baseline.
 """
 from __future__ import annotations
 
@@ -34,45 +35,65 @@ def split_regions(ni: int, nj: int, halo: int = 3, side: int = 32) -> Tuple[Rect
 
 
 class FvTransport:
-    """``exchange`` = "nccl" (packed strips + grouped NCCL send/recv, optionally overlapped with the
-    interior) or "p2p" (device barrier + one peer-memory pull kernel; ``q`` must then be the field of
-    the :class:`~b200stencil.halo.p2p.SymmetricField` given as ``symmetric_q``)."""
+    """One transport step on this GPU's batch of sub-domains.
+
+    ``exchange`` =
+      "device"  (the product path) the library-owned exchange of ``halo/device.py``: ONE kernel per halo update
+                (neighbour handshake + pull over NVLink peer memory).  ``q`` must be the field ``halo_exchange`` was
+                planned for (``HaloContext.field`` + ``HaloContext.plan``).  With ``overlap`` the exchange is forked onto
+                the context's stream and ``fv_tp2d_gated`` computes the halo-independent cells meanwhile, the rest once
+                the gate opens -- one stencil launch, no interior/frame split on the host;
+      "nccl"    (portable baseline, torch.distributed) packed strips + grouped NCCL send/recv, optionally overlapped
+                with an interior launch followed by four frame launches.
+    """
 
     def __init__(self, part: CubedSpherePartitioner, n_gpus: int, gpu: int, process_group=None,
-                 overlap: bool = True, side: int = 32, exchange: str = "nccl", symmetric_q=None, fused_signal: bool = False):
+                 overlap: bool = True, side: int = 32, exchange: str = "nccl", halo_exchange=None):
         self.part, self.n_gpus, self.gpu = part, n_gpus, gpu
         self.exchange = exchange
-        self.updater = HaloUpdater(part, n_gpus, gpu, process_group=process_group)
-        self.p2p = None
-        if exchange == "p2p":
-            from .p2p import P2PHaloUpdater
-
-            if symmetric_q is None:
-                raise ValueError('exchange="p2p" needs the SymmetricField that holds q')
-            self.p2p = P2PHaloUpdater(part, n_gpus, gpu, symmetric_q, fused_signal=fused_signal)  # fused: EXPERIMENTAL
-            overlap = False
-        self.overlap = overlap and bool(self.updater.plan.peers)
+        self.dev_exchange = None
+        self.updater = None
+        if exchange == "device":
+            if halo_exchange is None:
+                raise ValueError('exchange="device" needs the HaloExchange (HaloContext.plan) of the field that holds q')
+            self.dev_exchange = halo_exchange
+            self.overlap = bool(overlap)
+        elif exchange == "nccl":
+            self.updater = HaloUpdater(part, n_gpus, gpu, process_group=process_group)
+            self.overlap = overlap and bool(self.updater.plan.peers)
+        else:
+            raise ValueError(f"unknown exchange {exchange!r}: 'device' or 'nccl'")
         self.interior, self.frame = split_regions(part.nx, part.ny, part.halo, side)
         self._calls = {}
 
     def calls(self, q, crx, xfx, cry, yfx, rarea, q_out, q_out_halo: int = 0):
-        """(full, interior, [frame...]) PreparedCalls for this set of fields, marshalled once."""
+        """(full, interior, [frame...], gated) PreparedCalls for this set of fields, marshalled once."""
         fs = (q, crx, xfx, cry, yfx, rarea, q_out)
         key = tuple((t.data_ptr(), tuple(t.stride()), tuple(t.shape)) for t in fs) + (q_out_halo,)
         if key not in self._calls:
             mk = lambda region: stencils.prepare_fv_tp2d(*fs, region=region, q_out_halo=q_out_halo)  # noqa: E731
-            interior = mk(self.interior) if self.interior[1] > self.interior[0] else None
-            self._calls[key] = (mk(None), interior, [mk(r) for r in self.frame])
+            if self.dev_exchange is not None:
+                gated = stencils.prepare_fv_tp2d_gated(*fs, gate=self.dev_exchange.ctx.gate, q_out_halo=q_out_halo) if self.overlap else None
+                self._calls[key] = (mk(None), None, [], gated)
+            else:
+                interior = mk(self.interior) if self.interior[1] > self.interior[0] else None
+                self._calls[key] = (mk(None), interior, [mk(r) for r in self.frame], None)
         return self._calls[key]
 
     def step(self, q, crx, xfx, cry, yfx, rarea, q_out, q_out_halo: int = 0) -> None:
         """q (halo-padded batch field) -> q_out; q's halos are refreshed from the neighbours first."""
-        full, interior, frame = self.calls(q, crx, xfx, cry, yfx, rarea, q_out, q_out_halo)
-        if self.p2p is not None:
-            if q.data_ptr() != self.p2p.sfield.field.data_ptr():
-                raise ValueError("p2p exchange: q is not the symmetric field this transport was built for")
-            self.p2p.update()
-            full()
+        full, interior, frame, gated = self.calls(q, crx, xfx, cry, yfx, rarea, q_out, q_out_halo)
+        if self.dev_exchange is not None:
+            ex = self.dev_exchange
+            if q.data_ptr() != ex.field.data_ptr():
+                raise ValueError("device exchange: q is not the field this transport's HaloExchange was planned for")
+            if gated is not None:
+                ex.start(gated=True)
+                gated()
+                ex.wait()
+            else:
+                ex.update()
+                full()
             return
         if not self.overlap:
             self.updater.update(q)
@@ -94,22 +115,23 @@ class SplitTransport:
     The partitioner must have been built with ``corners=True``: corner blocks then arrive from the diagonal
     neighbour in the same exchange as the edge strips, and at the eight cube corners the exchange writes FV3's
     copy_corners values for x-sweeps while the kernel derives the y-sweep values itself (``corner_flags``).
-    ``exchange`` = "nccl" (packed strips, grouped send/recv) or "p2p" (peer-memory pull; ``symmetric_q`` holds q).
+    ``exchange`` = "nccl" (packed strips, grouped send/recv) or "device" (library-owned peer-memory exchange;
+    ``halo_exchange`` = the ``HaloContext.plan`` of the field that holds q).
     """
 
     def __init__(self, part: CubedSpherePartitioner, n_gpus: int, gpu: int, process_group=None, exchange: str = "nccl",
-                 symmetric_q=None):
+                 halo_exchange=None):
         if not part.corners:
             raise ValueError("fv_tp2d_split reads the halo corners: build the partitioner with corners=True")
         self.part, self.n_gpus, self.gpu = part, n_gpus, gpu
-        self.updater = HaloUpdater(part, n_gpus, gpu, process_group=process_group)
-        self.p2p = None
-        if exchange == "p2p":
-            from .p2p import P2PHaloUpdater
-
-            if symmetric_q is None:
-                raise ValueError('exchange="p2p" needs the SymmetricField that holds q')
-            self.p2p = P2PHaloUpdater(part, n_gpus, gpu, symmetric_q)
+        self.updater = None
+        self.dev_exchange = None
+        if exchange == "device":
+            if halo_exchange is None:
+                raise ValueError('exchange="device" needs the HaloExchange (HaloContext.plan) of the field that holds q')
+            self.dev_exchange = halo_exchange
+        else:
+            self.updater = HaloUpdater(part, n_gpus, gpu, process_group=process_group)
         nsub = part.subdomains_per_gpu(n_gpus)
         self.corner_flags_host = [part.cube_corner_flags(gpu * nsub + b) for b in range(nsub)]
         self._flags = {}
@@ -120,10 +142,10 @@ class SplitTransport:
         return self._flags[device]
 
     def step(self, q, crx, xfx, cry, yfx, area, rarea, q_out, fx_out=None, fy_out=None) -> None:
-        if self.p2p is not None:
-            if q.data_ptr() != self.p2p.sfield.field.data_ptr():
-                raise ValueError("p2p exchange: q is not the symmetric field this transport was built for")
-            self.p2p.update()
+        if self.dev_exchange is not None:
+            if q.data_ptr() != self.dev_exchange.field.data_ptr():
+                raise ValueError("device exchange: q is not the field this transport's HaloExchange was planned for")
+            self.dev_exchange.update()
         else:
             self.updater.update(q)
         stencils.fv_tp2d_split(q, crx, xfx, cry, yfx, area, rarea, q_out, fx_out, fy_out, corner_flags=self.corner_flags(q.device))

@@ -18,6 +18,7 @@ streams so the PCIe transfers of neighbouring chunks overlap the kernel.
 """
 from __future__ import annotations
 
+import os
 from math import prod
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -144,8 +145,15 @@ class FvTp2dHost:
             out[n] = base.as_strided((nb,) + tuple(proto.shape), (per,) + tuple(proto.stride()))
         return out
 
-    def __call__(self, host: Dict[str, torch.Tensor]) -> None:
-        """host['q_out'][b] <- fv_tp2d(host inputs [b]) for every b; returns when the data is on the host."""
+    def __call__(self, host: Dict[str, torch.Tensor], q_dev: Optional[torch.Tensor] = None, exchange=None, sync=None) -> None:
+        """host['q_out'][b] <- fv_tp2d(host inputs [b]) for every b; returns when the data is on the host.
+
+        With ``q_dev`` (a resident halo-padded batch field, e.g. ``HaloContext.field``) and ``exchange`` (a callable
+        that refreshes its halos on the current stream: ``HaloExchange.update`` or ``lambda: updater.update(q_dev)``)
+        the step includes the halo update: the whole of q is uploaded first, its halos are exchanged with the
+        neighbouring sub-domains / GPUs, and the per-sub-domain pipeline carries the other five inputs.
+        ``sync`` (e.g. ``HaloContext.barrier``) is called first when peers read ``q_dev``: nobody may still be pulling
+        the previous step's values while this step's upload overwrites them."""
         nb = host["q"].shape[0]
         cur = torch.cuda.current_stream(self.device)
         for s in (self.s_up, self.s_run, self.s_down):
@@ -154,12 +162,26 @@ class FvTp2dHost:
         run_done: List[torch.cuda.Event] = []
         down_done: List[Optional[torch.cuda.Event]] = [None, None]
         self.h2d_bytes = self.d2h_bytes = 0
+        names = self.NAMES
+        if q_dev is not None:
+            if sync is not None:
+                sync()
+            names = tuple(n for n in self.NAMES if n != "q")
+            with torch.cuda.stream(self.s_up):
+                for b in range(nb):
+                    self.h2d_bytes += copy_flat(q_dev[b], host["q"][b])
+                q_up = torch.cuda.Event()
+                q_up.record()
+            with torch.cuda.stream(self.s_run):
+                self.s_run.wait_event(q_up)
+                if exchange is not None:
+                    exchange()
         for b in range(nb):
             slot = self.slots[b & 1]
             with torch.cuda.stream(self.s_up):
                 if b >= 2:
                     self.s_up.wait_event(run_done[b - 2])  # inputs of this slot are free again
-                for n in self.NAMES:
+                for n in names:
                     self.h2d_bytes += copy_flat(slot[n], host[n][b])
                 ev = torch.cuda.Event()
                 ev.record()
@@ -168,7 +190,8 @@ class FvTp2dHost:
                 self.s_run.wait_event(up_done[b])
                 if down_done[b & 1] is not None:
                     self.s_run.wait_event(down_done[b & 1])  # q_out of this slot has been downloaded
-                stencils.fv_tp2d(slot["q"], slot["crx"], slot["xfx"], slot["cry"], slot["yfx"], slot["rarea"], slot["q_out"])
+                stencils.fv_tp2d(slot["q"] if q_dev is None else q_dev[b], slot["crx"], slot["xfx"], slot["cry"], slot["yfx"],
+                                 slot["rarea"], slot["q_out"])
                 ev = torch.cuda.Event()
                 ev.record()
                 run_done.append(ev)
@@ -180,3 +203,67 @@ class FvTp2dHost:
                 down_done[b & 1] = ev
         self.s_down.synchronize()
         cur.wait_stream(self.s_run)
+
+
+# ---- host placement and the link the e2e numbers are bounded by ---------------------------------------
+
+
+def _parse_cpulist(text: str) -> List[int]:
+    cpus: List[int] = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus += list(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def gpu_numa_node(device_index: int) -> Optional[int]:
+    """NUMA node the GPU hangs off (sysfs), or None when the platform does not say."""
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        return node if node >= 0 else None
+    except Exception:
+        return None
+
+
+def bind_to_gpu_numa_node(device_index: int) -> Optional[int]:
+    """Pin this process to the cores of the GPU's NUMA node, so that pinned host buffers allocated afterwards are
+    first-touched in the DRAM next to the GPU's PCIe root (one process per GPU: without it eight ranks can end up
+    streaming through one socket's memory controllers).  Returns the node, or None if nothing was changed."""
+    node = gpu_numa_node(device_index)
+    if node is None:
+        return None
+    try:
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set(_parse_cpulist(f.read())) & set(os.sched_getaffinity(0))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
+def measure_pcie(device, nbytes: int = 256 << 20, reps: int = 5) -> Dict[str, float]:
+    """Pinned host <-> device copy rate of this GPU's link in GB/s (best of ``reps``, CUDA events): the roofline of
+    every number measured with host-resident data."""
+    device = torch.device(device)
+    host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    dev = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    out = {}
+    for name, (dst, src) in {"h2d": (dev, host), "d2h": (host, dev)}.items():
+        best = 0.0
+        for _ in range(reps + 1):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            dst.copy_(src, non_blocking=True)
+            b.record()
+            b.synchronize()
+            best = max(best, nbytes / (a.elapsed_time(b) * 1e-3) / 1e9)
+        out[name] = round(best, 2)
+    out["bytes"] = nbytes
+    return out

@@ -29,6 +29,10 @@ int fv_tp2d(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j1, F3<c
             F3<const T> xfx, F3<const T> cry, F3<const T> yfx, F2<const T> rarea, F3<T> q_out, cudaStream_t s);
 
 template <typename T>
+int fv_tp2d_gated(int ni, int nj, int nk, int nb, F3<const T> q, F3<const T> crx, F3<const T> xfx, F3<const T> cry,
+                  F3<const T> yfx, F2<const T> rarea, int* gate, F3<T> q_out, cudaStream_t s);
+
+template <typename T>
 int fv_tp2d_split(int ni, int nj, int nk, int nb, F3<const T> q, F3<const T> crx, F3<const T> xfx, F3<const T> cry,
                   F3<const T> yfx, F2<const T> area, F2<const T> rarea, const int* corner_flags, F3<T> q_out,
                   F3<T> fx_out, F3<T> fy_out, cudaStream_t s);
@@ -53,9 +57,5 @@ int halo_move(int nlinks, int nk, int max_strip, const int64_t* links, const T* 
 
 template <typename T>
 int halo_pull(int nlinks, int nk, int max_strip, const int64_t* links, T* dst, cudaStream_t s);
-template <typename T>
-int halo_pull_sync(int nlinks, int nk, int max_strip, int my_rank, int world, const int64_t* links,
-                   const int64_t* peer_flags, int* sync_state, T* dst, cudaStream_t s);
-
 }  // namespace impl
 }  // namespace b2s

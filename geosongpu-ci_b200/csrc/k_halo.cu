@@ -130,56 +130,63 @@ int halo_pull(int nlinks, int nk, int max_strip, const int64_t* links, T* dst, c
 }
 
 // -------------------------------------------------------------------------------------------
-// halo_pull_sync (EXPERIMENTAL, opt-in through halo/p2p.py `fused_signal=True`; compiled and unit-tested on the
-// host side, NOT yet run on more than one GPU): halo_pull with the neighbour handshake inside the kernel, so a
-// halo update is ONE launch instead of torch's barrier kernel + halo_pull (at 8 GPUs the barrier and the extra
-// kernel boundary are ~10 of the ~25 us of fixed cost per 90 us step, profiles/README.md).
-//   * every rank owns an int32 flag array flags[world] in symmetric memory; peer_flags[r] is the address of
+// k_halo_exchange: the halo update of a b2s_halo context (csrc/halo_ctx.cu) as ONE launch -- halo_pull with the
+// neighbour handshake inside, so there is no separate barrier kernel and no NCCL call on the path.
+//   * every rank owns an int32 flag array flags[world] in peer-mapped memory; peer_flags[r] is the address of
 //     rank r's array as mapped into this process;
-//   * the step number (epoch) lives on the device (sync_state[0]), so a CUDA graph can replay the launch:
-//     every block reads it at entry, the last block to finish advances it (sync_state[1] counts blocks);
-//   * block (0,0,0) announces "my field is final for this epoch" to every peer: st.release.sys of the epoch
-//     into flags[my_rank] of each peer (the field was written by earlier kernels of this stream);
-//   * a block whose link reads a peer waits (ld.acquire.sys) until that peer's announcement has arrived, then
-//     pulls.  Announcements are monotonic, a rank can run at most one step ahead of a neighbour, and -- adjacency
-//     being symmetric -- a neighbour's announcement of epoch n+1 also says it has finished pulling epoch n from
-//     this rank, which is what a ping-pong time loop needs before overwriting the buffer;
-//   * no wait is unbounded: after ~2 s of spinning a block records status 1 in sync_state[2] and carries on
-//     (wrong halos, reported by the host, instead of a hung GPU).
+//   * the step number (epoch) lives on the device (state[0]), so a CUDA graph can replay the launch: every block
+//     reads it at entry, the last block to finish advances it (state[1] counts blocks);
+//   * block (0,0,0) announces "my field is final for this epoch" to every peer: st.release.sys of the epoch into
+//     flags[my_rank] of each peer (the field was written by earlier kernels in stream order);
+//   * a block whose link reads a peer waits (ld.acquire.sys on its OWN flag array, a local poll) until that peer's
+//     announcement has arrived, then pulls.  Announcements are monotonic, a rank can run at most one step ahead of
+//     a neighbour, and -- adjacency being symmetric -- a neighbour's announcement of epoch n+1 also says it has
+//     finished pulling epoch n from this rank, which is what a ping-pong time loop needs before overwriting;
+//   * gated: the last block raises state[8] (the gate, st.release.gpu) once every halo cell has been written;
+//     gated stencil kernels acquire it before their first load of a halo cell and lower it when they finish;
+//   * no wait is unbounded: after ~2 s of spinning a block records status 1 in state[2] and carries on
+//     (wrong halos, reported by b2s_halo_status, instead of a hung GPU).
+// Link words: 0..9 as halo_move, [10] base address of the source buffer, [11] owning rank (-1: this GPU).
 // -------------------------------------------------------------------------------------------
-static constexpr int kPullSyncWords = 12;
+static constexpr int kExchangeWords = 12;
 static constexpr long long kSyncTimeoutCycles = 4000000000LL;
+static constexpr int kGateWord = 8;
 
 __device__ __forceinline__ void st_release_sys(int* p, int v) { asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void st_release_gpu(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ int ld_acquire_sys(const int* p) {
   int v;
   asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 
-template <typename T, int KU>
-__global__ void __launch_bounds__(256) k_halo_pull_sync(int nk, const int64_t* __restrict__ links, T* dst, int my_rank, int world,
-                                                        const int64_t* __restrict__ peer_flags, int* sync_state) {
+template <typename T>
+__global__ void __launch_bounds__(256) k_halo_exchange(int nk, const int64_t* __restrict__ links, T* dst, int my_rank, int world,
+                                                       const int64_t* __restrict__ peer_flags, int* state, int gated) {
   __shared__ int s_epoch;
-  if (threadIdx.x == 0) s_epoch = *reinterpret_cast<volatile int*>(sync_state) + 1;
+  if (threadIdx.x == 0) s_epoch = *reinterpret_cast<volatile int*>(state) + 1;
   __syncthreads();
   const int epoch = s_epoch;
-  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (int)threadIdx.x < world && (int)threadIdx.x != my_rank)
+  if (world > 1 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (int)threadIdx.x < world && (int)threadIdx.x != my_rank) {
+    __threadfence_system();
     st_release_sys(reinterpret_cast<int*>(static_cast<uintptr_t>(peer_flags[threadIdx.x])) + my_rank, epoch);
+  }
 
-  const int64_t* L = links + (int64_t)blockIdx.z * kPullSyncWords;
+  const int64_t* L = links + (int64_t)blockIdx.z * kExchangeWords;
   const int src_rank = (int)L[11];
-  if (threadIdx.x == 0 && src_rank >= 0 && src_rank != my_rank) {
-    const int* mine = reinterpret_cast<const int*>(static_cast<uintptr_t>(peer_flags[my_rank])) + src_rank;
-    const long long t0 = clock64();
-    while (ld_acquire_sys(mine) < epoch) {
-      if (clock64() - t0 > kSyncTimeoutCycles) {
-        atomicExch(sync_state + 2, 1);
-        break;
+  if (src_rank >= 0 && src_rank != my_rank) {
+    if (threadIdx.x == 0) {
+      const int* mine = reinterpret_cast<const int*>(static_cast<uintptr_t>(peer_flags[my_rank])) + src_rank;
+      const long long t0 = clock64();
+      while (ld_acquire_sys(mine) < epoch) {
+        if (clock64() - t0 > kSyncTimeoutCycles) {
+          atomicExch(state + 2, 1);
+          break;
+        }
       }
     }
+    __syncthreads();
   }
-  __syncthreads();
 
   const int nd = (int)L[8], np = (int)L[9];
   const int t = blockIdx.x * 256 + threadIdx.x;
@@ -188,37 +195,54 @@ __global__ void __launch_bounds__(256) k_halo_pull_sync(int nk, const int64_t* _
     const int64_t ssd = L[1], ssp = L[2], ssk = L[3], dsk = L[7];
     int d, p;
     strip_decode(t, nd, np, ssd, d, p);
-    const int k0 = blockIdx.y * KU;
-    copy_levels<T, KU>(src + (L[0] + d * ssd + p * ssp + k0 * ssk), ssk, dst + (L[4] + d * L[5] + p * L[6] + k0 * dsk), dsk, nk - k0);
+    const int k0 = blockIdx.y;
+    dst[L[4] + d * L[5] + p * L[6] + k0 * dsk] = src[L[0] + d * ssd + p * ssp + k0 * ssk];
   }
 
-  // the last block to finish advances the epoch for the next launch (or graph replay)
+  // the last block to finish publishes the halos (gate) and advances the epoch for the next launch / graph replay
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
     const int total = (int)(gridDim.x * gridDim.y * gridDim.z);
-    if (atomicAdd(sync_state + 1, 1) == total - 1) {
-      sync_state[1] = 0;
+    if (atomicAdd(state + 1, 1) == total - 1) {
+      state[1] = 0;
       __threadfence();
-      *reinterpret_cast<volatile int*>(sync_state) = epoch;
+      *reinterpret_cast<volatile int*>(state) = epoch;
+      if (gated) st_release_gpu(state + kGateWord, 1);
     }
   }
 }
 
-template <typename T>
-int halo_pull_sync(int nlinks, int nk, int max_strip, int my_rank, int world, const int64_t* links, const int64_t* peer_flags,
-                   int* sync_state, T* dst, cudaStream_t s) {
-  B2S_ARGCHECK(nlinks > 0 && nk > 0 && max_strip > 0, "halo_pull_sync: bad sizes nlinks=%d nk=%d max_strip=%d", nlinks, nk, max_strip);
-  B2S_ARGCHECK(world >= 1 && world <= 256 && my_rank >= 0 && my_rank < world, "halo_pull_sync: rank %d of %d", my_rank, world);
-  B2S_ARGCHECK(links && peer_flags && sync_state && dst, "halo_pull_sync: null pointer");
-  B2S_ARGCHECK(nk <= 65535 && nlinks <= 65535, "halo_pull_sync: grid too large (nk=%d, nlinks=%d)", nk, nlinks);
-  dim3 grid((max_strip + 255) / 256, nk, nlinks);
-  k_halo_pull_sync<T, 1><<<grid, 256, 0, s>>>(nk, links, dst, my_rank, world, peer_flags, sync_state);
-  return check_launch("halo_pull_sync");
+// an exchange without links still has to announce, advance the epoch and raise the gate
+__global__ void k_halo_exchange_empty(int my_rank, int world, const int64_t* __restrict__ peer_flags, int* state, int gated) {
+  const int epoch = *reinterpret_cast<volatile int*>(state) + 1;
+  if ((int)threadIdx.x < world && (int)threadIdx.x != my_rank) {
+    __threadfence_system();
+    st_release_sys(reinterpret_cast<int*>(static_cast<uintptr_t>(peer_flags[threadIdx.x])) + my_rank, epoch);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    *reinterpret_cast<volatile int*>(state) = epoch;
+    if (gated) st_release_gpu(state + kGateWord, 1);
+  }
 }
 
-template int halo_pull_sync<double>(int, int, int, int, int, const int64_t*, const int64_t*, int*, double*, cudaStream_t);
-template int halo_pull_sync<float>(int, int, int, int, int, const int64_t*, const int64_t*, int*, float*, cudaStream_t);
+int halo_exchange_launch(int elem_size, int nlinks, int nk, int max_strip, int my_rank, int world, const int64_t* links,
+                         const int64_t* peer_flags, int* state, void* dst, int gated, cudaStream_t s) {
+  B2S_ARGCHECK(world >= 1 && world <= 64 && my_rank >= 0 && my_rank < world, "halo_exchange: rank %d of %d", my_rank, world);
+  B2S_ARGCHECK(peer_flags && state, "halo_exchange: null pointer");
+  if (nlinks == 0) {
+    k_halo_exchange_empty<<<1, 64, 0, s>>>(my_rank, world, peer_flags, state, gated);
+    return check_launch("halo_exchange");
+  }
+  B2S_ARGCHECK(nk > 0 && max_strip > 0 && links && dst, "halo_exchange: bad sizes nlinks=%d nk=%d max_strip=%d", nlinks, nk, max_strip);
+  dim3 grid((max_strip + 255) / 256, nk, nlinks);
+  if (elem_size == 8)
+    k_halo_exchange<double><<<grid, 256, 0, s>>>(nk, links, static_cast<double*>(dst), my_rank, world, peer_flags, state, gated);
+  else
+    k_halo_exchange<float><<<grid, 256, 0, s>>>(nk, links, static_cast<float*>(dst), my_rank, world, peer_flags, state, gated);
+  return check_launch("halo_exchange");
+}
 
 template int halo_pull<double>(int, int, int, const int64_t*, double*, cudaStream_t);
 template int halo_pull<float>(int, int, int, const int64_t*, float*, cudaStream_t);

@@ -46,6 +46,36 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
 
+// ---- halo gate (csrc/halo_ctx.cu, k_halo.cu k_halo_exchange) -----------------------------------
+// gate[0]: raised (st.release.gpu) by the exchange kernel when every halo cell has been written; gate[1]: CTAs of the
+// consuming stencil that have issued all their loads; gate[2]: status (1 = a wait gave up).  The producer lane of a
+// gated stencil acquires gate[0] before its first TMA load that touches a halo cell; the cells were written through
+// the generic proxy by another kernel and are read through the async proxy, hence the proxy fence.  Bounded spin: a
+// protocol error becomes a status word (b2s_halo_status), not a hung GPU.
+__device__ __forceinline__ void gate_acquire(int* gate) {
+  int v;
+  const long long t0 = clock64();
+  for (;;) {
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(gate) : "memory");
+    if (v != 0) break;
+    if (clock64() - t0 > 4000000000LL) {
+      atomicExch(gate + 2, 1);
+      break;
+    }
+    __nanosleep(64);
+  }
+  asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+// called by one thread per CTA after the CTA's last load: the last CTA lowers the gate for the next exchange
+__device__ __forceinline__ void gate_release(int* gate, int nctas) {
+  __threadfence();
+  if (atomicAdd(gate + 1, 1) == nctas - 1) {
+    gate[1] = 0;
+    __threadfence();
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(gate), "r"(0) : "memory");
+  }
+}
+
 // cp.async (LDGSTS): one naturally aligned element global -> shared without a register round trip
 template <int BYTES>
 __device__ __forceinline__ void cp_async(void* dst, const void* src) {

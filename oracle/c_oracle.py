@@ -158,3 +158,10 @@ class COracle:
         if w is None:
             w = np.empty(tuple(reversed(b.shape)), dtype=b.dtype).transpose()
         self._fn("tridiag", b)(_INT(ni), _INT(nj), _INT(nk), *_f3(a), *_f3(b), *_f3(c), *_f3(d), *_f3(w), *_f3(x))
+
+    def halo_move(self, links: np.ndarray, nk: int, src: np.ndarray, dst: np.ndarray):
+        """Run a 10-word link table (halo/partitioner.py links as laid out by halo/updater.py HaloPlan.tables) on flat
+        host storage: the CPU restatement of the CUDA halo_move kernel."""
+        links = np.ascontiguousarray(links, dtype=np.int64).reshape(-1, 10)
+        assert src.dtype == dst.dtype and src.ndim == 1 and dst.ndim == 1
+        self._fn("halo_move", src)(_INT(len(links)), _INT(nk), _P(links.ctypes.data), _P(src.ctypes.data), _P(dst.ctypes.data))

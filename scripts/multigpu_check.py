@@ -1,8 +1,15 @@
 #!/usr/bin/env python
-"""Multi-GPU correctness check, run under torchrun (one rank per GPU):
-  1. global-id halo exchange over NCCL: every halo cell holds its geometric neighbour's id;
-  2. the overlapped transport step (interior | exchange, then frame) equals exchange-then-full-stencil bit for bit.
+"""Multi-GPU correctness check, run under torchrun (one rank per GPU); prints one line per check and a final
+JSON line, exits non-zero on the first failure.  Every wait on the device is bounded, so a protocol error shows up
+here as an exception, not as a hung GPU.
+
+  1. library-owned exchange (b2s_halo_init / alloc / plan / exchange over NVLink peer memory, csrc/halo_ctx.cu):
+     global-id field, every halo cell must hold its geometric neighbour's id -- three epochs, edges and corners;
+  2. the overlapped transport step (exchange forked + fv_tp2d_gated) == exchange-then-stencil, eagerly and from a
+     replayed CUDA graph, with both TMA kernels;
+  3. NCCL baseline: packed-strip exchange adjacency, and NCCL step == device-exchange step bit for bit.
 """
+import json
 import os
 import sys
 
@@ -13,8 +20,9 @@ for p in (ROOT, os.path.join(ROOT, "geosongpu-ci_b200"), os.path.join(ROOT, "tes
 import torch
 import torch.distributed as dist
 
-from b200stencil import fields, stencils
-from b200stencil.halo.partitioner import CubedSpherePartitioner, layout_for
+from b200stencil import _abi, fields
+from b200stencil.halo.device import HaloContext
+from b200stencil.halo.partitioner import CubedSpherePartitioner, global_id_field, layout_for
 from b200stencil.halo.transport import FvTransport
 from b200stencil.halo.updater import HaloUpdater
 from halo_util import batch_field, check_field
@@ -22,79 +30,102 @@ from halo_util import batch_field, check_field
 
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
-    dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
-    N, nk = 96, 5
-    part = CubedSpherePartitioner(N, layout_for(world))
-    f = batch_field(part, world, rank, nk, device=dev, pad=2)
-    up = HaloUpdater(part, world, rank)
-    up.update(f)
-    torch.cuda.synchronize()
-    check_field(part, world, rank, f, nk)
+    results = {}
 
+    def say(msg):
+        if rank == 0:
+            print(f"multigpu_check ok on {world} GPUs: {msg}", flush=True)
+
+    ctx = HaloContext(rank, world, local)  # session name broadcast through torch.distributed (bootstrap only)
+    for corners in (False, True):
+        N, nk = 96, 5
+        part = CubedSpherePartitioner(N, layout_for(world), corners=corners)
+        nsub, ni, nj = part.subdomains_per_gpu(world), part.nx, part.ny
+        f = ctx.field((ni + 6, nj + 6, nk), nsub, torch.float64)
+        ex = ctx.plan(f, part)
+        for rep in range(3):
+            for b in range(nsub):
+                f[b].copy_(torch.from_numpy(global_id_field(part, rank * nsub + b, nk)))
+            torch.cuda.synchronize()
+            ctx.barrier()
+            if rep == 1:
+                ex.start()
+                ex.wait()
+            else:
+                ex.update()
+            torch.cuda.synchronize()
+            ctx.check()
+            check_field(part, world, rank, f, nk)
+            ctx.barrier()
+        say(f"device exchange adjacency, corners={corners}, 3 epochs, {ex.remote_bytes} B over NVLink per update")
+    results["device_exchange_adjacency"] = "ok"
+
+    # ---- transport steps ----
+    N, nk = 384, 4
+    part = CubedSpherePartitioner(N, layout_for(world))
     nsub, ni, nj = part.subdomains_per_gpu(world), part.nx, part.ny
     g = torch.Generator(device=dev).manual_seed(7 + rank)
     mk = lambda s, lo, hi: fields.empty(s, torch.float64, dev, batch=nsub).uniform_(lo, hi, generator=g)  # noqa: E731
-    q = mk((ni + 6, nj + 6, nk), 0.5, 1.5)
+    q = ctx.field((ni + 6, nj + 6, nk), nsub, torch.float64)
+    q.uniform_(0.5, 1.5, generator=g)
+    ex = ctx.plan(q, part)
     crx, cry = mk((ni + 1, nj, nk), -0.9, 0.9), mk((ni, nj + 1, nk), -0.9, 0.9)
     xfx, yfx, rarea = mk((ni + 1, nj, nk), -1, 1), mk((ni, nj + 1, nk), -1, 1), mk((ni, nj), 0.9, 1.1)
-    q2 = q.clone()
-    o1 = fields.zeros((ni, nj, nk), device=dev, batch=nsub)
-    o2 = fields.zeros((ni, nj, nk), device=dev, batch=nsub)
-    FvTransport(part, world, rank, overlap=True).step(q, crx, xfx, cry, yfx, rarea, o1)
-    FvTransport(part, world, rank, overlap=False).step(q2, crx, xfx, cry, yfx, rarea, o2)
+    q_nccl = fields.empty((ni + 6, nj + 6, nk), torch.float64, dev, batch=nsub)
+    q_nccl.copy_(q)
+    o_serial = fields.zeros((ni, nj, nk), device=dev, batch=nsub)
+    FvTransport(part, world, rank, exchange="device", halo_exchange=ex, overlap=False).step(q, crx, xfx, cry, yfx, rarea, o_serial)
     torch.cuda.synchronize()
-    assert torch.equal(q, q2), "halos differ between the overlapped and the plain exchange"
-    assert torch.equal(o1, o2), f"overlap vs plain: max diff {(o1 - o2).abs().max().item()}"
-    dist.barrier()
-    if rank == 0:
-        print(f"multigpu_check ok on {world} GPUs: NCCL halo adjacency + overlapped step == plain step", flush=True)
-
-    # ---- peer-memory path: one pull kernel over NVLink ----
-    from b200stencil.halo.p2p import P2PHaloUpdater, SymmetricField
-    from b200stencil.halo.partitioner import global_id_field
-
-    sf = SymmetricField((ni + 6, nj + 6, nk), nsub, torch.float64, dev)
-    for b in range(nsub):
-        sf.field[b].copy_(torch.from_numpy(global_id_field(part, rank * nsub + b, nk)))
-    torch.cuda.synchronize()
-    dist.barrier()
-    P2PHaloUpdater(part, world, rank, sf).update()
-    torch.cuda.synchronize()
-    check_field(part, world, rank, sf.field, nk)
-    # p2p transport step == nccl transport step
-    sf.field.copy_(q2)
-    sf.field[:, :3, 3:-3] = -1.0  # scrub the west halo strips (not the corners) so the pull has to refill them
-    torch.cuda.synchronize()
-    dist.barrier()
-    o3 = fields.zeros((ni, nj, nk), device=dev, batch=nsub)
-    FvTransport(part, world, rank, exchange="p2p", symmetric_q=sf).step(sf.field, crx, xfx, cry, yfx, rarea, o3)
-    torch.cuda.synchronize()
-    assert torch.equal(sf.field, q2), "p2p halos differ from the NCCL exchange"
-    assert torch.equal(o3, o2), "p2p step differs from the NCCL step"
-    dist.barrier()
-    if rank == 0:
-        print(f"multigpu_check ok on {world} GPUs: peer-memory halo_pull adjacency + p2p step == NCCL step", flush=True)
-
-    # ---- EXPERIMENTAL one-launch handshake + pull (halo_pull_sync): only with B2S_CHECK_FUSED=1.  Three updates in a
-    #      row exercise the device-resident epoch; every wait in the kernel is bounded (status word), so a protocol
-    #      error shows up as an exception here, not as a hung GPU.
-    if os.environ.get("B2S_CHECK_FUSED") == "1":
-        fused = P2PHaloUpdater(part, world, rank, sf, fused_signal=True)
+    ctx.check()
+    for variant in (2, 3):
+        _abi.set_option("fv_variant", variant)
+        tr = FvTransport(part, world, rank, exchange="device", halo_exchange=ex, overlap=True)
         for rep in range(3):
-            for b in range(nsub):
-                sf.field[b].copy_(torch.from_numpy(global_id_field(part, rank * nsub + b, nk)))
+            o = fields.zeros((ni, nj, nk), device=dev, batch=nsub)
+            tr.step(q, crx, xfx, cry, yfx, rarea, o)
             torch.cuda.synchronize()
-            dist.barrier()
-            fused.update()
-            torch.cuda.synchronize()
-            fused.check()
-            check_field(part, world, rank, sf.field, nk)
-            dist.barrier()
-        assert int(fused.sync_state[0].item()) == 3 and int(fused.sync_state[1].item()) == 0
-        if rank == 0:
-            print(f"multigpu_check ok on {world} GPUs: fused handshake + pull (halo_pull_sync), 3 epochs", flush=True)
+            assert torch.equal(o, o_serial), f"gated step (variant {variant}, rep {rep}) differs: {(o - o_serial).abs().max().item()}"
+        o = fields.zeros((ni, nj, nk), device=dev, batch=nsub)
+        cap = torch.cuda.Stream(device=dev)
+        cap.wait_stream(torch.cuda.current_stream(dev))
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=cap):
+            tr.step(q, crx, xfx, cry, yfx, rarea, o)
+        for rep in range(5):
+            o.zero_()
+            graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(o, o_serial), f"graph replay of the gated step (variant {variant}) differs"
+        ctx.check()
+        del graph
+    _abi.set_option("fv_variant", 0)
+    say("overlapped step (exchange || fv_tp2d_gated) == exchange-then-stencil, tile + streaming kernels, eager + graph replay")
+    results["gated_step"] = "ok"
+
+    # ---- NCCL baseline ----
+    f = batch_field(CubedSpherePartitioner(96, layout_for(world)), world, rank, 5, device=dev, pad=2)
+    HaloUpdater(CubedSpherePartitioner(96, layout_for(world)), world, rank).update(f)
+    torch.cuda.synchronize()
+    check_field(CubedSpherePartitioner(96, layout_for(world)), world, rank, f, 5)
+    o_nccl = fields.zeros((ni, nj, nk), device=dev, batch=nsub)
+    o_nccl2 = fields.zeros((ni, nj, nk), device=dev, batch=nsub)
+    FvTransport(part, world, rank, overlap=True).step(q_nccl, crx, xfx, cry, yfx, rarea, o_nccl)
+    FvTransport(part, world, rank, overlap=False).step(q_nccl, crx, xfx, cry, yfx, rarea, o_nccl2)
+    torch.cuda.synchronize()
+    assert torch.equal(o_nccl, o_nccl2), "NCCL overlapped vs plain step differ"
+    assert torch.equal(q_nccl[:, :, 3:-3], q[:, :, 3:-3]) and torch.equal(q_nccl[:, 3:-3], q[:, 3:-3]), "NCCL halos differ from the device exchange"
+    assert torch.equal(o_nccl, o_serial), "NCCL step differs from the device-exchange step"
+    say("NCCL baseline adjacency; NCCL step == device-exchange step bit for bit")
+    results["nccl_equals_device"] = "ok"
+
+    dist.barrier()
+    ctx.finalize()
+    if rank == 0:
+        print(json.dumps({"multigpu_check": "ok", "n_gpus": world, **results}), flush=True)
     sys.stdout.flush()
     os._exit(0)
 

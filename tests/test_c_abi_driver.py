@@ -14,6 +14,24 @@ LIBDIR = os.path.join(ROOT, "geosongpu-ci_b200", "b200stencil", "lib")
 CUDA = os.environ.get("CUDA_HOME", "/usr/local/cuda")
 
 
+def _compile(tmp_path_factory, name, extra=()):
+    src = os.path.join(ROOT, "tests", "c_abi", name + ".c")
+    exe = str(tmp_path_factory.mktemp("c_abi") / name)
+    cmd = ["gcc", "-O1", "-Wall", "-Wextra", "-Werror", src, "-I", os.path.join(ROOT, "include"), "-I", os.path.join(CUDA, "include"),
+           "-L", LIBDIR, "-lb200stencil", "-L", os.path.join(CUDA, "lib64"), "-lcudart", *extra, "-o", exe]  # fmt: skip
+    subprocess.run(cmd, check=True, capture_output=True, text=True)
+    env = dict(os.environ, LD_LIBRARY_PATH=os.pathsep.join([LIBDIR, os.path.join(CUDA, "lib64"), os.environ.get("LD_LIBRARY_PATH", "")]))
+    return exe, env
+
+
+@pytest.fixture(scope="module")
+def halo_driver(tmp_path_factory):
+    """tests/c_abi/halo_driver.c: the b2s_halo_* lifecycle with two ranks (threads) and no Python in the process."""
+    if shutil.which("gcc") is None or not os.path.exists(os.path.join(CUDA, "include", "cuda_runtime_api.h")):
+        pytest.skip("gcc or the CUDA runtime headers are not available")
+    return _compile(tmp_path_factory, "halo_driver", ("-lpthread",))
+
+
 @pytest.fixture(scope="module")
 def driver(tmp_path_factory):
     if shutil.which("gcc") is None or not os.path.exists(os.path.join(CUDA, "include", "cuda_runtime_api.h")):
@@ -51,3 +69,20 @@ def test_compiled_caller_reproduces_the_golden_vectors(driver):
     r = subprocess.run([exe], env=env, capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
     assert "abi_driver ok" in r.stdout
+
+
+@pytest.mark.skipif(_has_cuda(), reason="this is the no-GPU behaviour")
+def test_halo_driver_fails_loudly_without_a_gpu(halo_driver):
+    exe, env = halo_driver
+    r = subprocess.run([exe], env=env, capture_output=True, text=True, timeout=60)
+    assert r.returncode == 3, (r.returncode, r.stdout, r.stderr)
+    assert "b2s_init" in r.stderr and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+def test_halo_lifecycle_from_c(halo_driver):
+    """Two ranks, symmetric allocation, plain and forked exchanges, gated stencil, finalize -- all through the C-ABI."""
+    exe, env = halo_driver
+    r = subprocess.run([exe], env=env, capture_output=True, text=True, timeout=180)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "halo_driver ok" in r.stdout

@@ -198,33 +198,33 @@ def test_halo_exchange_gloo(world):
     mp.spawn(_gloo_worker, args=(world, _free_port(), 12, 2), nprocs=world, join=True)
 
 
-def test_pull_tables_name_the_owner_of_every_strip():
-    """halo/p2p.py build_pull_table: the 12-word table of the (experimental) one-launch exchange is the 11-word table
-    plus the rank that owns each source strip; -1 marks strips of sub-domains on the same GPU (nothing to wait for)."""
+def test_plan_tables_name_the_owner_of_every_strip():
+    """halo/device.py build_plan_table (the host table of b2s_halo_plan): 12 words per link, [10] = session rank that
+    owns the source strip, offsets relative to the field; the device-side handshake relies on adjacency being symmetric
+    (whoever I wait for also waits for me), and every halo cell must be covered exactly once."""
     import torch
 
     from b200stencil import fields
-    from b200stencil.halo import p2p
-    from b200stencil.halo.updater import FieldGeometry
+    from b200stencil.halo import device
 
-    for n_gpus in (2, 4, 8):
+    for n_gpus in (1, 2, 4, 8):
         part = CubedSpherePartitioner(24, layout_for(n_gpus), 3)
         nsub = part.subdomains_per_gpu(n_gpus)
         f = fields.empty((part.nx + 6, part.ny + 6, 5), torch.float64, "cpu", batch=nsub)
-        geo = FieldGeometry(f, 3)
-        ptrs = [1000 * (r + 1) for r in range(n_gpus)]
+        ranks = [(3 * g + 1) % n_gpus for g in range(n_gpus)] if n_gpus in (2, 4, 8) else [0]  # a non-identity rank map
         neighbours = {}
         for gpu in range(n_gpus):
-            t11, b11 = p2p.build_pull_table(part, n_gpus, gpu, geo, 8, ptrs, list(range(n_gpus)))
-            t12, b12 = p2p.build_pull_table(part, n_gpus, gpu, geo, 8, ptrs, list(range(n_gpus)), with_source_rank=True)
-            assert t11.shape[1] == p2p.PULL_WORDS and t12.shape[1] == p2p.PULL_SYNC_WORDS
-            assert np.array_equal(t11, t12[:, :11]) and b11 == b12
-            assert len(t12) >= 4 * nsub  # at least one strip per edge of every sub-domain
-            for row in t12:
-                owner = int(row[11])
-                assert row[10] == ptrs[gpu if owner < 0 else owner] and owner != gpu
-            neighbours[gpu] = {int(r) for r in t12[:, 11] if r >= 0}
-        # the handshake relies on adjacency being symmetric: whoever I wait for also waits for me
-        for a, ns_ in neighbours.items():
-            for b in ns_:
-                assert a in neighbours[b]
+            t = device.build_plan_table(part, n_gpus, gpu, f, ranks)
+            assert t.shape[1] == device.PLAN_WORDS and t.dtype == np.int64
+            assert len(t) >= 4 * nsub  # at least one strip per edge of every sub-domain
+            assert set(int(r) for r in t[:, 10]) <= set(ranks) and np.all(t[:, 11] == 0)
+            neighbours[ranks[gpu]] = {int(r) for r in t[:, 10] if r != ranks[gpu]}
+            # destination cells: every edge-halo cell of every local sub-domain exactly once, none in the interior
+            hits = np.zeros(f.numel() + 64, dtype=np.int32)
+            for L in t:
+                d, p = np.meshgrid(np.arange(L[8]), np.arange(L[9]), indexing="ij")
+                np.add.at(hits, (L[4] + d * L[5] + p * L[6]).ravel(), 1)
+            assert hits.max() == 1 and hits.sum() == nsub * 2 * 3 * (part.nx + part.ny)
+        for a_, ns_ in neighbours.items():
+            for b_ in ns_:
+                assert a_ in neighbours[b_]
