@@ -207,8 +207,11 @@ def main(argv=None) -> int:
                     help="fv (default, the contract line): fv_tp2d transport step on C384x72; chain: BASELINE configs[4], "
                          "fv_tp2d + pe_prefix + remap on C720x137; patterns: BASELINE configs[1], the dsl_patterns column "
                          "stencils on C96x72 (separate reports, see run_chain / run_patterns)")
-    ap.add_argument("--no-overlap", action="store_true", help="exchange, then compute (no halo-independent-cells-first overlap)")
-    ap.add_argument("--overlap", action="store_true", help="force the overlapped (gated) step also at N = 1")
+    ap.add_argument("--step", choices=["auto", "fused", "overlap", "serial"], default="auto",
+                    help="how the device-exchange step is launched: fused = ONE kernel (b2s_halo_fv_tp2d: the stencil grid shares the "
+                         "exchange among its CTAs first, then computes behind per-sub-domain gates); overlap = exchange kernel forked "
+                         "beside one gated stencil launch; serial = exchange kernel, then stencil; auto = fused")
+    ap.add_argument("--no-overlap", action="store_true", help="same as --step serial (and no interior/frame overlap on the NCCL baseline)")
     ap.add_argument("--halo", choices=["auto", "device", "nccl"], default="auto",
                     help="halo exchange: device (= auto) the library-owned exchange, ONE kernel per update (neighbour handshake "
                          "+ pull over NVLink peer memory, b2s_halo_*), forked next to a gated stencil launch; nccl = the "
@@ -274,7 +277,7 @@ def main(argv=None) -> int:
     mk = lambda s, lo, hi: fields.empty(s, dtype, dev, batch=nsub).uniform_(lo, hi, generator=g)  # noqa: E731
     use_device = ns.halo in ("auto", "device")
     ctx = HaloContext(rank, world, local_rank)
-    overlap = (not ns.no_overlap) and (world > 1 or ns.overlap)
+    step_mode = "serial" if ns.no_overlap else ("fused" if ns.step == "auto" else ns.step)
 
     # ---- halo_check: the exchange the timed loop uses, on a global-id field, every halo cell against geometry ----
     halo_check = None
@@ -305,7 +308,7 @@ def main(argv=None) -> int:
         q = ctx.field((ni + 6, nj + 6, NK), nsub, dtype)
         q.uniform_(0.5, 1.5, generator=g)
         ex = ctx.plan(q, part)
-        tr = FvTransport(part, n_gpus, rank, exchange="device", halo_exchange=ex, overlap=overlap)
+        tr = FvTransport(part, n_gpus, rank, exchange="device", halo_exchange=ex, overlap=step_mode != "serial", fused=step_mode == "fused")
     else:
         q = mk((ni + 6, nj + 6, NK), 0.5, 1.5)
         ex = None
@@ -404,7 +407,7 @@ def main(argv=None) -> int:
     if ex is not None:
         ctx.check()  # no device-side wait timed out during the timed regions
     if ex is not None:
-        launches_per_step = 2  # k_halo_exchange + fv_tp2d (gated or plain)
+        launches_per_step = 1 if tr.fused else 2  # the fused step is one launch; else k_halo_exchange + fv_tp2d (gated or plain)
     else:
         launches_per_step = (1 if not tr.updater.plan.peers else 3) + (1 if not tr.overlap else 1 + len(tr.frame))
     launches = regions * K * launches_per_step if graph is not None else _abi.launch_count() - launches0
@@ -539,8 +542,11 @@ def main(argv=None) -> int:
                 "subdomains_per_gpu": nsub, "subdomain": [ni, nj], "overlap_exchange": bool(tr.overlap),
                 "launch": "cuda-graph replay of the whole step" if graph is not None else "eager launches",
                 "l2": f"inputs larger than L2: {input_mb:.0f} MB of inputs per GPU per step vs 126 MB L2, no flush needed",
-                "halo_exchange": ("device: one k_halo_exchange launch (neighbour handshake + pull over NVLink peer memory, b2s_halo_*)"
-                                  + (", forked beside one gated fv_tp2d launch (halo-independent cells first)" if tr.overlap else ", then fv_tp2d")
+                "step_launch": (step_mode if ex is not None else "nccl"),
+                "halo_exchange": (("device, fused: ONE kernel per step (b2s_halo_fv_tp2d) -- neighbour handshake + pull over NVLink peer memory "
+                                   "shared among the CTAs of the stencil grid, then fv_tp2d behind per-sub-domain gates" if tr.fused else
+                                   "device: one k_halo_exchange launch (neighbour handshake + pull over NVLink peer memory, b2s_halo_*)"
+                                   + (", forked beside one gated fv_tp2d launch (sub-domain b computed while the halos of b+1.. arrive)" if tr.overlap else ", then fv_tp2d"))
                                   if ex is not None else
                                   "nccl baseline: pack kernel + grouped NCCL send/recv + unpack kernel" if n_gpus > 1 else
                                   "local halo_move kernel"),
@@ -617,8 +623,9 @@ def run_chain(ns) -> int:
     pe2[..., -1] = pe1[..., -1]
     q_adv = fields.empty((ni, nj, nk), dtype, dev, batch=nsub)
     q_new = fields.empty((ni, nj, nk), dtype, dev, batch=nsub)
-    chain = DycoreChain(FvTransport(part, world, rank, overlap=world > 1 and not ns.no_overlap, exchange=exchange, halo_exchange=ex),
-                        fused=ns.fused_remap)
+    step_mode = "serial" if ns.no_overlap else ("fused" if ns.step == "auto" else ns.step)
+    chain = DycoreChain(FvTransport(part, world, rank, overlap=step_mode != "serial", fused=step_mode == "fused", exchange=exchange,
+                                    halo_exchange=ex), fused=ns.fused_remap)
     args = (q, crx, xfx, cry, yfx, rarea, delp, pe2, q_adv, pe1, q_new)
 
     def barrier():
@@ -663,7 +670,7 @@ def run_chain(ns) -> int:
             "data": "synthetic",
             "config": {"workload": "dycore chain on C720x137 (BASELINE configs[4])", "subdomains_per_gpu": nsub,
                        "subdomain": [ni, nj], "halo_exchange": "device (k_halo_exchange, b2s_halo_*)",
-                       "overlap_exchange": world > 1 and not ns.no_overlap,
+                       "step_launch": step_mode,
                        "launch": "cuda-graph replay" if graph is not None else "eager launches",
                        "vertical": "remap_delp (pe_prefix fused into remap)" if ns.fused_remap else "pe_prefix + remap"},
             "roofline": {"bound": "hbm", "achieved": round(gbs, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",

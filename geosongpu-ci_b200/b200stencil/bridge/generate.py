@@ -285,6 +285,7 @@ RUNTIME_SYMBOLS = [
     "b2s_halo_exchange_wait",
     "b2s_halo_gate",
     "b2s_halo_status",
+    "b2s_halo_trace",
 ]
 
 RUNTIME_CDEF = """
@@ -312,6 +313,7 @@ int b2s_halo_exchange_start(int64_t ctx, int plan, int gated, void* stream);
 int b2s_halo_exchange_wait(int64_t ctx, void* stream);
 int b2s_halo_gate(int64_t ctx, int** gate);
 int b2s_halo_status(int64_t ctx, int* epoch, int* status);
+int b2s_halo_trace(int64_t ctx, int64_t* out6);
 """
 
 HEADER_PROLOGUE = """/* b200stencil.h -- C-ABI of libb200stencil.so (GENERATED, do not edit).
@@ -387,22 +389,26 @@ B2S_API int b2s_halo_free(int64_t ctx, void* ptr);
 /* address, in this process, of rank `peer`'s copy of the byte `ptr` points to (ptr inside a b2s_halo_alloc buffer) */
 B2S_API int b2s_halo_peer_ptr(int64_t ctx, const void* ptr, int peer, void** peer_ptr);
 /* bind a link table to a field.  links: HOST int64[nlinks][12]; words 0..9 as for b2s_halo_move (element offsets
- * relative to `field`, the same on every rank), [10] = rank that owns the source sub-domain, [11] = 0. */
+ * relative to `field`, the same on every rank), [10] = rank that owns the source sub-domain, [11] = destination
+ * sub-domain (batch index of the field, < 64; 0 for an unbatched field). */
 B2S_API int b2s_halo_plan(int64_t ctx, const void* field, int elem_size, int nk, int nlinks, const int64_t* links, int* plan);
 B2S_API int64_t b2s_halo_plan_remote_bytes(int64_t ctx, int plan);
 /* halo update = ONE kernel (neighbour handshake + pull over peer memory).  b2s_halo_exchange runs it on `stream`;
  * _start forks it onto the context's own high-priority stream (ordered after the work already on `stream`), _wait
  * joins: what the caller enqueues on `stream` in between overlaps the exchange.  Both can be captured in a CUDA graph.
- * gated != 0: the kernel raises the gate when the halos are complete; exactly one gated stencil launch
- * (b2s_fv_tp2d_gated_c) must consume it between _start and _wait. */
+ * gated != 0: the kernel opens gate[b] when the halos of sub-domain b are complete (b = 0, 1, ... in turn); exactly one
+ * gated stencil launch (b2s_fv_tp2d_gated_c, same batch) must consume the gates between _start and _wait. */
 B2S_API int b2s_halo_exchange(int64_t ctx, int plan, void* stream);
 B2S_API int b2s_halo_exchange_start(int64_t ctx, int plan, int gated, void* stream);
 B2S_API int b2s_halo_exchange_wait(int64_t ctx, void* stream);
-/* device address of the gate words (int32[4]) for gated stencil launches */
+/* device address of the gate words (int32[66]: one flag per sub-domain, CTA counter, status) for gated stencil launches */
 B2S_API int b2s_halo_gate(int64_t ctx, int** gate);
 /* host-synchronising: exchanges completed; status bit 0 = a neighbour's announcement timed out on the device,
  * bit 1 = a gated stencil gave up waiting for the gate */
 B2S_API int b2s_halo_status(int64_t ctx, int* epoch, int* status);
+/* diagnostics, host-synchronising: device timeline (ns) of the last exchange + gated stencil: exchange start, exchange end,
+ * gate 0 opened, first stencil CTA started, stencil CTA 0 passed gate 0, last stencil CTA finished */
+B2S_API int b2s_halo_trace(int64_t ctx, int64_t* out6);
 int b2s_halo_init(const char* session, int rank, int world, int device, int64_t* ctx);
 int b2s_halo_finalize(int64_t ctx);
 int b2s_halo_rank(int64_t ctx);
@@ -418,6 +424,7 @@ int b2s_halo_exchange_start(int64_t ctx, int plan, int gated, void* stream);
 int b2s_halo_exchange_wait(int64_t ctx, void* stream);
 int b2s_halo_gate(int64_t ctx, int** gate);
 int b2s_halo_status(int64_t ctx, int* epoch, int* status);
+int b2s_halo_trace(int64_t ctx, int64_t* out6);
 """
 
 HEADER_EPILOGUE = """#ifdef __cplusplus

@@ -9,8 +9,9 @@ Rendezvous, peer mapping, the neighbour handshake and the pull all live behind t
 * turns the partitioner's links into the host table ``b2s_halo_plan`` wants.
 
 A halo update is ONE kernel (handshake + pull).  ``start()`` forks it onto the context's own stream so it overlaps
-whatever the caller launches before ``wait()``; with ``gated=True`` a gated stencil (``stencils.fv_tp2d_gated``)
-computes the cells that read no halo while the exchange is in flight and the rest once the gate opens.
+whatever the caller launches before ``wait()``; with ``gated=True`` the kernel opens one gate per sub-domain as its
+halos land and a gated stencil (``stencils.prepare_fv_tp2d_gated``) computes sub-domain b while the halos of b+1..
+are still in flight.
 A C or Fortran caller drives the same entry points without Python (tests/c_abi/abi_driver.c).
 """
 from __future__ import annotations
@@ -110,11 +111,11 @@ class HaloContext:
     # ---- exchange -------------------------------------------------------------------------------
     @property
     def gate(self) -> torch.Tensor:
-        """int32[4] device words the gated stencils poll (``b2s_halo_gate``)."""
+        """int32[66] device words the gated stencils poll (``b2s_halo_gate``): one flag per sub-domain, CTA counter, status."""
         if self._gate is None:
             p = self._ffi.new("int**")
             _abi.check("b2s_halo_gate", self._lib.b2s_halo_gate(self.handle, p))
-            self._gate = self._tensor(int(self._ffi.cast("uintptr_t", p[0])), 16, torch.int32)
+            self._gate = self._tensor(int(self._ffi.cast("uintptr_t", p[0])), 66 * 4, torch.int32)
         return self._gate
 
     def plan(self, field: torch.Tensor, part: CubedSpherePartitioner, n_gpus: Optional[int] = None, gpu: Optional[int] = None,
@@ -142,6 +143,14 @@ class HaloContext:
         _abi.check("b2s_halo_status", self._lib.b2s_halo_status(self.handle, e, s))
         return int(e[0]), int(s[0])
 
+    def trace(self):
+        """Device timeline (ns, relative to the exchange start) of the last exchange + gated stencil; diagnostics."""
+        out = self._ffi.new("int64_t[6]")
+        _abi.check("b2s_halo_trace", self._lib.b2s_halo_trace(self.handle, out))
+        t = [int(out[i]) for i in range(6)]
+        names = ("exchange_start", "exchange_end", "gate0_open", "stencil_start", "stencil_gate0", "stencil_end")
+        return {n: (v - t[0] if v else None) for n, v in zip(names, t)}
+
     def check(self) -> None:
         epoch, status = self.status()
         if status:
@@ -156,7 +165,8 @@ class HaloContext:
 
 
 def build_plan_table(part: CubedSpherePartitioner, n_gpus: int, gpu: int, field: torch.Tensor, ranks: Sequence[int]) -> np.ndarray:
-    """int64 [nlinks, 12] host table of ``b2s_halo_plan``: element offsets relative to ``field``'s first element."""
+    """int64 [nlinks, 12] host table of ``b2s_halo_plan``: element offsets relative to ``field``'s first element,
+    [10] = session rank owning the source sub-domain, [11] = destination sub-domain (batch index)."""
     from .updater import FieldGeometry
 
     geo = FieldGeometry(field, part.halo)
@@ -169,7 +179,7 @@ def build_plan_table(part: CubedSpherePartitioner, n_gpus: int, gpu: int, field:
         rows.append([
             geo.cell(b_src, l.si0, l.sj0), geo.step(l.sdi, l.sdj), geo.step(l.spi, l.spj), geo.sk,
             geo.cell(b_dst, l.di0, l.dj0), geo.step(l.ddi, l.ddj), geo.step(l.dpi, l.dpj), geo.sk,
-            l.nd, l.np_, int(ranks[owner]), 0,
+            l.nd, l.np_, int(ranks[owner]), b_dst,
         ])  # fmt: skip
     return np.asarray(rows, dtype=np.int64).reshape(-1, PLAN_WORDS)
 

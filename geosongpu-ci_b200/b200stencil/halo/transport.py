@@ -2,9 +2,9 @@
 
 This is the unit bench.py times (BASELINE config 4: "FV3-style horizontal finite-volume
 flux/advection stencil with 3-point halo on C384x72, halo exchange at 2/4/8 GPUs").  The exchange runs
-on its own stream while the cells whose stencil never reads a halo cell are computed; the cells along
-the edges follow once the halos have landed -- inside ONE gated stencil launch on the product path
-(library-owned exchange, halo/device.py), as an interior launch + frame launches on the NCCL baseline.
+on its own stream.  Product path (library-owned exchange, halo/device.py): ONE gated stencil launch that
+computes sub-domain b as soon as its halos have landed while those of the next sub-domains are still in
+flight.  NCCL baseline: an interior launch beside the exchange, then frame launches.
 """
 from __future__ import annotations
 
@@ -41,23 +41,28 @@ class FvTransport:
       "device"  (the product path) the library-owned exchange of ``halo/device.py``: ONE kernel per halo update
                 (neighbour handshake + pull over NVLink peer memory).  ``q`` must be the field ``halo_exchange`` was
                 planned for (``HaloContext.field`` + ``HaloContext.plan``).  With ``overlap`` the exchange is forked onto
-                the context's stream and ``fv_tp2d_gated`` computes the halo-independent cells meanwhile, the rest once
-                the gate opens -- one stencil launch, no interior/frame split on the host;
+                the context's stream and opens one gate per sub-domain as its halos land; ``fv_tp2d_gated`` walks the
+                batch in the same order, so sub-domain b is computed while the halos of b+1.. are in flight -- one
+                stencil launch, its DRAM-friendly item order untouched (interior-cells-first was measured: it costs
+                13-28 % of the stencil, profiles/r02_overlap.md).  With ``fused`` the whole step is ONE launch
+                (``b2s_halo_fv_tp2d``): the CTAs of the stencil grid share the exchange among themselves first;
       "nccl"    (portable baseline, torch.distributed) packed strips + grouped NCCL send/recv, optionally overlapped
                 with an interior launch followed by four frame launches.
     """
 
     def __init__(self, part: CubedSpherePartitioner, n_gpus: int, gpu: int, process_group=None,
-                 overlap: bool = True, side: int = 32, exchange: str = "nccl", halo_exchange=None):
+                 overlap: bool = True, side: int = 32, exchange: str = "nccl", halo_exchange=None, fused: bool = False):
         self.part, self.n_gpus, self.gpu = part, n_gpus, gpu
         self.exchange = exchange
         self.dev_exchange = None
         self.updater = None
+        self.fused = False
         if exchange == "device":
             if halo_exchange is None:
                 raise ValueError('exchange="device" needs the HaloExchange (HaloContext.plan) of the field that holds q')
             self.dev_exchange = halo_exchange
-            self.overlap = bool(overlap)
+            self.fused = bool(fused)
+            self.overlap = bool(overlap) or self.fused
         elif exchange == "nccl":
             self.updater = HaloUpdater(part, n_gpus, gpu, process_group=process_group)
             self.overlap = overlap and bool(self.updater.plan.peers)
@@ -73,7 +78,12 @@ class FvTransport:
         if key not in self._calls:
             mk = lambda region: stencils.prepare_fv_tp2d(*fs, region=region, q_out_halo=q_out_halo)  # noqa: E731
             if self.dev_exchange is not None:
-                gated = stencils.prepare_fv_tp2d_gated(*fs, gate=self.dev_exchange.ctx.gate, q_out_halo=q_out_halo) if self.overlap else None
+                if self.fused:
+                    gated = stencils.prepare_halo_fv_tp2d(self.dev_exchange, *fs, q_out_halo=q_out_halo)
+                elif self.overlap:
+                    gated = stencils.prepare_fv_tp2d_gated(*fs, gate=self.dev_exchange.ctx.gate, q_out_halo=q_out_halo)
+                else:
+                    gated = None
                 self._calls[key] = (mk(None), None, [], gated)
             else:
                 interior = mk(self.interior) if self.interior[1] > self.interior[0] else None
@@ -87,7 +97,9 @@ class FvTransport:
             ex = self.dev_exchange
             if q.data_ptr() != ex.field.data_ptr():
                 raise ValueError("device exchange: q is not the field this transport's HaloExchange was planned for")
-            if gated is not None:
+            if self.fused:
+                gated()
+            elif gated is not None:
                 ex.start(gated=True)
                 gated()
                 ex.wait()

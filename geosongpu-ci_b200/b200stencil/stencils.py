@@ -121,16 +121,36 @@ def _expect_fv(fn, q, crx, xfx, cry, yfx, rarea, q_out, ni, nj, nk, q_out_halo=0
 
 
 def prepare_fv_tp2d_gated(q, crx, xfx, cry, yfx, rarea, q_out, gate, q_out_halo: int = 0) -> "_abi.PreparedCall":
-    """fv_tp2d on the whole domain overlapped with the halo update of ``q`` in flight (``HaloExchange.start(gated=True)``):
-    cells whose stencil reads no halo first, the rest once ``gate`` (``HaloContext.gate``) opens.  Same bits as fv_tp2d."""
+    """fv_tp2d on the whole batch overlapped with the halo update of ``q`` in flight (``HaloExchange.start(gated=True)``):
+    sub-domain b is computed once ``gate[b]`` (``HaloContext.gate``) says its halos have landed, while those of b+1..
+    are still arriving.  ``q`` must be the whole batch field of the exchange.  Same bits as fv_tp2d."""
     h = FV_HALO
     nip, njp, nk, nb = shape3(q)
     ni, nj = nip - 2 * h, njp - 2 * h
     _expect_fv("fv_tp2d_gated", q, crx, xfx, cry, yfx, rarea, q_out, ni, nj, nk, q_out_halo)
-    _expect_flat("fv_tp2d_gated", "gate", gate, 4, torch.int32)
+    _expect_flat("fv_tp2d_gated", "gate", gate, 66, torch.int32)
     return _abi.prepare(
         "fv_tp2d_gated", _abi.precision_of(q),
         dict(ni=ni, nj=nj, nk=nk, nb=nb, q=q, crx=crx, xfx=xfx, cry=cry, yfx=yfx, rarea=rarea, gate=gate, q_out=q_out),
+        origins={"q": (h, h, 0), "q_out": (q_out_halo, q_out_halo, 0)},
+    )  # fmt: skip
+
+
+def prepare_halo_fv_tp2d(halo_exchange, q, crx, xfx, cry, yfx, rarea, q_out, q_out_halo: int = 0) -> "_abi.PreparedCall":
+    """The transport step as ONE launch (``b2s_halo_fv_tp2d``): halo update of ``q`` over NVLink peer memory fused with
+    fv_tp2d on the whole batch -- every CTA of the persistent stencil grid first takes its share of the exchange
+    (neighbour handshake + strip copies), then walks its stencil items in sub-domain order behind the gates the
+    exchange opens.  ``halo_exchange`` = the ``HaloContext.plan`` of ``q``.  Same bits as exchange-then-fv_tp2d."""
+    h = FV_HALO
+    nip, njp, nk, nb = shape3(q)
+    ni, nj = nip - 2 * h, njp - 2 * h
+    _expect_fv("halo_fv_tp2d", q, crx, xfx, cry, yfx, rarea, q_out, ni, nj, nk, q_out_halo)
+    if q.data_ptr() != halo_exchange.field.data_ptr():
+        raise ValueError("halo_fv_tp2d: q is not the field the HaloExchange was planned for")
+    return _abi.prepare(
+        "halo_fv_tp2d", _abi.precision_of(q),
+        dict(ctx=halo_exchange.ctx.handle, plan=halo_exchange.plan, ni=ni, nj=nj, nk=nk, nb=nb, crx=crx, xfx=xfx, cry=cry, yfx=yfx,
+             rarea=rarea, q=q, q_out=q_out),
         origins={"q": (h, h, 0), "q_out": (q_out_halo, q_out_halo, 0)},
     )  # fmt: skip
 

@@ -24,6 +24,7 @@
 #include <time.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cerrno>
 #include <cstdio>
@@ -37,10 +38,14 @@
 #include "../../include/b200stencil.h"
 #include "impl.cuh"
 
+#include "halo_device.cuh"
+
 namespace b2s {
 namespace impl {
-int halo_exchange_launch(int elem_size, int nlinks, int nk, int max_strip, int my_rank, int world, const int64_t* links,
-                         const int64_t* peer_flags, int* state, void* dst, int gated, cudaStream_t s);
+int halo_exchange_launch(int elem_size, int nb, const HaloXchg& X, cudaStream_t s);
+template <typename T>
+int fv_tp2d_fused(int ni, int nj, int nk, int nb, F3<const T> q, F3<const T> crx, F3<const T> xfx, F3<const T> cry,
+                  F3<const T> yfx, F2<const T> rarea, F3<T> q_out, const HaloXchg& xchg, cudaStream_t s);
 }
 }  // namespace b2s
 
@@ -50,8 +55,9 @@ namespace {
 
 constexpr int kMaxRanks = 64;
 constexpr uint32_t kMagic = 0xB2005A10u;
-constexpr int kStateWords = 16;  // device state: [0] epoch [1] blocks done [2] status; gate at [8..11]
-constexpr int kGateOffset = 8;   // gate words: [0] halos ready [1] consumer CTAs done [2] consumer status
+constexpr int kStateWords = 256;  // device state: [0] epoch [1] blocks done [2] status; [32 + b] blocks done of sub-domain b
+constexpr int kGateOffset = 128;  // gate words: [b] halos of sub-domain b ready, [64] consumer CTAs done, [65] consumer status
+constexpr int kGateSlots = 64;
 
 struct Slot {
   cudaIpcMemHandle_t handle;
@@ -80,8 +86,9 @@ struct Allocation {
 };
 
 struct Plan {
-  int64_t* links_dev = nullptr;  // [nlinks, 12]
-  int nlinks = 0, nk = 0, max_strip = 0, elem_size = 0;
+  int64_t* links_dev = nullptr;  // [nlinks, 12], sorted by destination sub-domain
+  int* b_total_dev = nullptr;    // [kGateSlots] exchange work units (link, level) per destination sub-domain
+  int nlinks = 0, nk = 0, max_strip = 0, elem_size = 0, nb = 0;
   void* field = nullptr;
   int64_t remote_bytes = 0;
 };
@@ -323,8 +330,10 @@ extern "C" int b2s_halo_finalize(int64_t ctx) {
   cudaDeviceSynchronize();
   int rc = B2S_OK;
   if (c->seg && !c->seg->failed.load()) rc = rdv_barrier(c, "b2s_halo_finalize");  // no peer still pulls from my buffers
-  for (auto& p : c->plans)
+  for (auto& p : c->plans) {
     if (p.links_dev) cudaFree(p.links_dev);
+    if (p.b_total_dev) cudaFree(p.b_total_dev);
+  }
   for (auto& a : c->allocs) sym_free(c, a);
   if (c->peer_flags_dev) cudaFree(c->peer_flags_dev);
   if (c->state) cudaFree(c->state);
@@ -391,7 +400,8 @@ extern "C" int b2s_halo_peer_ptr(int64_t ctx, const void* ptr, int peer, void** 
 }
 
 // links: HOST array [nlinks, 12] int64 -- words 0..9 as for b2s_halo_move (offsets in elements relative to `field`, the
-// same on every rank: the allocation is symmetric), [10] = rank that owns the source sub-domain, [11] = 0 (reserved).
+// same on every rank: the allocation is symmetric), [10] = rank that owns the source sub-domain, [11] = destination
+// sub-domain (batch index of the field, < 64; 0 when the field is not batched).
 extern "C" int b2s_halo_plan(int64_t ctx, const void* field, int elem_size, int nk, int nlinks, const int64_t* links, int* plan_out) {
   B2S_CTX(c, ctx, "b2s_halo_plan");
   if (!plan_out || !field || (elem_size != 4 && elem_size != 8) || nk <= 0 || nk > 65535 || nlinks < 0 || nlinks > 65535 || (nlinks && !links))
@@ -403,20 +413,33 @@ extern "C" int b2s_halo_plan(int64_t ctx, const void* field, int elem_size, int 
   DeviceGuard guard(c->device);
   Plan p;
   p.nlinks = nlinks, p.nk = nk, p.elem_size = elem_size, p.field = const_cast<void*>(field);
+  // stable sort by destination sub-domain (the gates of a gated exchange open in that order), and inside a sub-domain
+  // the strips read from this GPU before those read from peers: the copies that need no announcement go first
+  std::vector<int> order(nlinks);
+  for (int n = 0; n < nlinks; ++n) order[n] = n;
+  auto key = [&](int x) { return links[(size_t)x * 12 + 11] * 2 + (links[(size_t)x * 12 + 10] != c->rank ? 1 : 0); };
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return key(x) < key(y); });
   std::vector<int64_t> tbl((size_t)nlinks * 12);
+  std::vector<int> per_b(kGateSlots, 0);
   for (int n = 0; n < nlinks; ++n) {
-    const int64_t* L = links + (size_t)n * 12;
-    const int64_t owner = L[10];
-    if (owner < 0 || owner >= c->world) return set_error(B2S_EINVAL, "b2s_halo_plan: link %d names owner rank %lld of %d", n, (long long)owner, c->world);
-    if (L[8] <= 0 || L[9] <= 0) return set_error(B2S_EINVAL, "b2s_halo_plan: link %d has an empty strip", n);
+    const int64_t* L = links + (size_t)order[n] * 12;
+    const int64_t owner = L[10], dst_b = L[11];
+    if (owner < 0 || owner >= c->world) return set_error(B2S_EINVAL, "b2s_halo_plan: link %d names owner rank %lld of %d", order[n], (long long)owner, c->world);
+    if (dst_b < 0 || dst_b >= kGateSlots) return set_error(B2S_EINVAL, "b2s_halo_plan: link %d names destination sub-domain %lld (0 .. %d)", order[n], (long long)dst_b, kGateSlots - 1);
+    if (L[8] <= 0 || L[9] <= 0) return set_error(B2S_EINVAL, "b2s_halo_plan: link %d has an empty strip", order[n]);
     int64_t* D = tbl.data() + (size_t)n * 12;
     memcpy(D, L, 10 * sizeof(int64_t));
     const char* base = a ? static_cast<const char*>(a->peers[owner]) + off : static_cast<const char*>(field);
     D[10] = (int64_t) reinterpret_cast<intptr_t>(base);
-    D[11] = owner == c->rank ? -1 : owner;
+    D[11] = (owner == c->rank ? 0 : owner + 1) | (dst_b << 16);
     if (L[8] * L[9] > p.max_strip) p.max_strip = (int)(L[8] * L[9]);
     if (owner != c->rank) p.remote_bytes += L[8] * L[9] * nk * elem_size;
+    per_b[dst_b] += 1;
+    if (dst_b + 1 > p.nb) p.nb = (int)dst_b + 1;
   }
+  for (int& v : per_b) v *= nk;  // work units (link, level) per destination sub-domain
+  B2S_CUDA(cudaMalloc(&p.b_total_dev, kGateSlots * sizeof(int)), "b2s_halo_plan: cudaMalloc");
+  B2S_CUDA(cudaMemcpy(p.b_total_dev, per_b.data(), kGateSlots * sizeof(int), cudaMemcpyHostToDevice), "b2s_halo_plan: cudaMemcpy");
   if (nlinks) {
     B2S_CUDA(cudaMalloc(&p.links_dev, tbl.size() * sizeof(int64_t)), "b2s_halo_plan: cudaMalloc");
     B2S_CUDA(cudaMemcpy(p.links_dev, tbl.data(), tbl.size() * sizeof(int64_t), cudaMemcpyHostToDevice), "b2s_halo_plan: cudaMemcpy");
@@ -431,12 +454,40 @@ extern "C" int64_t b2s_halo_plan_remote_bytes(int64_t ctx, int plan) {
   return (c && plan >= 0 && plan < (int)c->plans.size()) ? c->plans[plan].remote_bytes : -1;
 }
 
+static impl::HaloXchg xchg_of(const HaloCtx* c, const Plan& p, int gated) {
+  impl::HaloXchg X;
+  X.links = p.links_dev, X.peer_flags = c->peer_flags_dev, X.b_total = p.b_total_dev, X.state = c->state, X.dst = p.field;
+  X.nlinks = p.nlinks, X.nk = p.nk, X.my_rank = c->rank, X.world = c->world, X.gated = gated;
+  return X;
+}
+
 static int launch_exchange(HaloCtx* c, int plan, int gated, cudaStream_t s) {
   if (plan < 0 || plan >= (int)c->plans.size()) return set_error(B2S_EINVAL, "b2s_halo_exchange: plan %d of %d", plan, (int)c->plans.size());
   const Plan& p = c->plans[plan];
-  return impl::halo_exchange_launch(p.elem_size, p.nlinks, p.nk, p.max_strip, c->rank, c->world, p.links_dev, c->peer_flags_dev, c->state,
-                                    p.field, gated, s);
+  return impl::halo_exchange_launch(p.elem_size, p.nb, xchg_of(c, p, gated), s);
 }
+
+// The transport step as ONE launch: halo update of the plan's field (neighbour handshake + strip copies over peer
+// memory, taken in shares by the CTAs of the stencil grid) fused with fv_tp2d on the whole batch behind per-sub-domain
+// gates.  q must be the plan's field (its compute cell (0,0,0): the pointer b2s_fv_tp2d takes).
+template <typename T>
+int b2s::impl::halo_fv_tp2d(int64_t ctx, int plan, int ni, int nj, int nk, int nb, F3<const T> crx, F3<const T> xfx, F3<const T> cry,
+                            F3<const T> yfx, F2<const T> rarea, F3<T> q, F3<T> q_out, cudaStream_t s) {
+  B2S_CTX(c, ctx, "b2s_halo_fv_tp2d");
+  if (plan < 0 || plan >= (int)c->plans.size()) return set_error(B2S_EINVAL, "b2s_halo_fv_tp2d: plan %d of %d", plan, (int)c->plans.size());
+  const Plan& p = c->plans[plan];
+  B2S_ARGCHECK(q.p != nullptr && p.elem_size == (int)sizeof(T) && p.nk == nk && p.nb <= nb,
+               "b2s_halo_fv_tp2d: the plan is for %d-byte elements, %d levels, %d sub-domains; the call has %d, %d, %d", p.elem_size,
+               p.nk, p.nb, (int)sizeof(T), nk, nb);
+  B2S_ARGCHECK(static_cast<const void*>(q.p - 3 - 3 * q.sj) == p.field, "b2s_halo_fv_tp2d: q is not the field the plan was made for");
+  DeviceGuard guard(c->device);
+  if (p.nlinks == 0) return set_error(B2S_EINVAL, "b2s_halo_fv_tp2d: the plan has no links; call b2s_fv_tp2d");
+  return impl::fv_tp2d_fused<T>(ni, nj, nk, nb, F3<const T>{q.p, q.sj, q.sk, q.sb}, crx, xfx, cry, yfx, rarea, q_out, xchg_of(c, p, 1), s);
+}
+template int b2s::impl::halo_fv_tp2d<double>(int64_t, int, int, int, int, int, F3<const double>, F3<const double>, F3<const double>,
+                                             F3<const double>, F2<const double>, F3<double>, F3<double>, cudaStream_t);
+template int b2s::impl::halo_fv_tp2d<float>(int64_t, int, int, int, int, int, F3<const float>, F3<const float>, F3<const float>,
+                                            F3<const float>, F2<const float>, F3<float>, F3<float>, cudaStream_t);
 
 // Halo update of the plan's field on `stream` itself (no fork): handshake + pull in one kernel.
 extern "C" int b2s_halo_exchange(int64_t ctx, int plan, void* stream) {
@@ -474,11 +525,23 @@ extern "C" int b2s_halo_exchange_wait(int64_t ctx, void* stream) {
   return B2S_OK;
 }
 
-// Device address of the gate words (int32[4]: halos ready, consumer CTAs done, consumer status, reserved).
+// Device address of the gate words (int32[66]: [b] halos of sub-domain b ready, [64] consumer CTAs done, [65] status).
 extern "C" int b2s_halo_gate(int64_t ctx, int** gate) {
   B2S_CTX(c, ctx, "b2s_halo_gate");
   if (!gate) return set_error(B2S_EINVAL, "b2s_halo_gate: NULL");
   *gate = c->state + kGateOffset;
+  return B2S_OK;
+}
+
+// Diagnostics, host-synchronising: device timeline (globaltimer, ns) of the LAST exchange and gated stencil --
+// out[0] exchange start, [1] exchange end, [2] gate 0 opened, [3] first stencil CTA started, [4] stencil CTA 0 passed
+// gate 0, [5] last stencil CTA finished.  Slots never written are 0.
+extern "C" int b2s_halo_trace(int64_t ctx, int64_t* out6) {
+  B2S_CTX(c, ctx, "b2s_halo_trace");
+  if (!out6) return set_error(B2S_EINVAL, "b2s_halo_trace: NULL");
+  DeviceGuard guard(c->device);
+  B2S_CUDA(cudaDeviceSynchronize(), "b2s_halo_trace: cudaDeviceSynchronize");
+  B2S_CUDA(cudaMemcpy(out6, c->state + 200, 6 * sizeof(int64_t), cudaMemcpyDeviceToHost), "b2s_halo_trace: cudaMemcpy");
   return B2S_OK;
 }
 
@@ -491,6 +554,6 @@ extern "C" int b2s_halo_status(int64_t ctx, int* epoch, int* status) {
   B2S_CUDA(cudaDeviceSynchronize(), "b2s_halo_status: cudaDeviceSynchronize");
   B2S_CUDA(cudaMemcpy(h, c->state, sizeof(h), cudaMemcpyDeviceToHost), "b2s_halo_status: cudaMemcpy");
   if (epoch) *epoch = h[0];
-  if (status) *status = (h[2] ? 1 : 0) | (h[kGateOffset + 2] ? 2 : 0);
+  if (status) *status = (h[2] ? 1 : 0) | (h[kGateOffset + kGateSlots + 1] ? 2 : 0);
   return B2S_OK;
 }

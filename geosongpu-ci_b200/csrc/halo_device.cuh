@@ -1,0 +1,144 @@
+// Device side of the library-owned halo exchange (csrc/halo_ctx.cu): the strip copy with the neighbour handshake inside,
+// as a __device__ function so that it can run as its own kernel (k_halo.cu k_halo_exchange) or as the first phase of a
+// stencil kernel (k_fv_tma.cu / k_fv_stream.cu, b2s_halo_fv_tp2d: halo update + transport in ONE launch).
+#pragma once
+#include "common.cuh"
+
+namespace b2s {
+namespace impl {
+
+// Everything the exchange needs, by value in kernel parameters.  links == nullptr: no exchange.
+struct HaloXchg {
+  const int64_t* links;       // [nlinks, 12], sorted by destination sub-domain
+  const int64_t* peer_flags;  // [world] address of every rank's int32 flag array as mapped here
+  const int* b_total;         // [64] work units (link, level) per destination sub-domain
+  int* state;                 // [0] epoch, [1] blocks done, [2] status, [32 + b] units done, [128 + b] gate b, [200..] timeline
+  void* dst;                  // this rank's field
+  int nlinks, nk, my_rank, world, gated;
+};
+
+static constexpr int kExchangeWords = 12;
+static constexpr long long kSyncTimeoutCycles = 4000000000LL;
+static constexpr int kDoneWord = 32;
+static constexpr int kGateWord = 128;
+static constexpr int kTraceWord = 200;  // uint64 timeline slots (tma.cuh gate_trace): [0] start, [1] end, [2] gate 0 opened
+
+__device__ __forceinline__ void trace_ns(int* state, int slot) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  reinterpret_cast<unsigned long long*>(state + kTraceWord)[slot] = t;
+}
+__device__ __forceinline__ void st_release_sys(int* p, int v) { asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void st_release_gpu(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void strip_decode(int t, int nd, int np, int64_t ssd, int& d, int& p) {
+  if (ssd == 1 || ssd == -1) {  // depth runs along i on the source side
+    d = t % nd;
+    p = t / nd;
+  } else {
+    p = t % np;
+    d = t / np;
+  }
+}
+
+// Called by EVERY thread of EVERY block of the grid (it contains block barriers).  A work unit is one (link, level)
+// strip; block j takes units j, j + gridDim.x, ... in link order, so sub-domains complete -- and their gates open --
+// one after the other.  Protocol: see k_halo.cu.
+// s_scratch: one int of shared memory (the caller's, so that kernels with a dynamic TMA window keep it unpadded).
+template <typename T>
+__device__ __forceinline__ void halo_exchange_body(const HaloXchg& X, int* s_scratch) {
+  const int nthreads = blockDim.x;
+  int* state = X.state;
+  if (threadIdx.x == 0) *s_scratch = *reinterpret_cast<volatile int*>(state) + 1;
+  __syncthreads();
+  const int epoch = *s_scratch;
+  if (X.world > 1 && blockIdx.x == 0) {
+    for (int r = threadIdx.x; r < X.world; r += nthreads)
+      if (r != X.my_rank) {
+        __threadfence_system();
+        st_release_sys(reinterpret_cast<int*>(static_cast<uintptr_t>(X.peer_flags[r])) + X.my_rank, epoch);
+      }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) trace_ns(state, 0);
+  unsigned long long arrived = 0ull;  // peers whose announcement of this epoch has been seen (block-uniform)
+  const int nk = X.nk, units = X.nlinks * nk;
+  T* dst = static_cast<T*>(X.dst);
+  int cur_b = -1, cur_n = 0;  // units of sub-domain cur_b this block has copied and not yet reported
+  // report: every thread's stores of those units are done (block barrier), visible device-wide (fence), counted; the
+  // block that completes a sub-domain's count opens its gate
+  auto report = [&]() {
+    if (!X.gated || cur_n == 0) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(state + kDoneWord + cur_b, cur_n) + cur_n == X.b_total[cur_b]) {
+        state[kDoneWord + cur_b] = 0;
+        st_release_gpu(state + kGateWord + cur_b, 1);
+        if (cur_b == 0) trace_ns(state, 2);
+      }
+    }
+  };
+  for (int u = blockIdx.x; u < units; u += gridDim.x) {
+    const int link = u / nk, k0 = u - link * nk;
+    const int64_t* L = X.links + (int64_t)link * kExchangeWords;
+    const int src_rank = (int)(L[11] & 0xffff) - 1, dst_b = (int)(L[11] >> 16);
+    if (dst_b != cur_b) {
+      report();
+      cur_b = dst_b, cur_n = 0;
+    }
+    if (src_rank >= 0 && src_rank != X.my_rank && !((arrived >> src_rank) & 1ull)) {
+      if (threadIdx.x == 0) {
+        const int* mine = reinterpret_cast<const int*>(static_cast<uintptr_t>(X.peer_flags[X.my_rank])) + src_rank;
+        const long long t0 = clock64();
+        while (ld_acquire_sys(mine) < epoch) {
+          if (clock64() - t0 > kSyncTimeoutCycles) {
+            atomicExch(state + 2, 1);
+            break;
+          }
+        }
+      }
+      __syncthreads();
+      arrived |= 1ull << src_rank;
+    }
+    const int nd = (int)L[8], np = (int)L[9], n = nd * np;
+    const T* src = reinterpret_cast<const T*>(static_cast<uintptr_t>(L[10])) + (L[0] + k0 * L[3]);
+    T* out = dst + (L[4] + k0 * L[7]);
+    const int64_t ssd = L[1], ssp = L[2], dsd = L[5], dsp = L[6];
+    for (int t0 = threadIdx.x; t0 < n; t0 += 4 * nthreads) {  // four independent loads in flight per thread
+      T v[4];
+      int d[4], p[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int t = t0 + i * nthreads;
+        if (t < n) {
+          strip_decode(t, nd, np, ssd, d[i], p[i]);
+          v[i] = src[d[i] * ssd + p[i] * ssp];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (t0 + i * nthreads < n) out[d[i] * dsd + p[i] * dsp] = v[i];
+    }
+    ++cur_n;
+  }
+  report();
+  // the last block of the launch advances the epoch for the next launch / graph replay
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(state + 1, 1) == (int)gridDim.x - 1) {
+      state[1] = 0;
+      trace_ns(state, 1);
+      __threadfence();
+      *reinterpret_cast<volatile int*>(state) = epoch;
+    }
+  }
+}
+
+}  // namespace impl
+}  // namespace b2s

@@ -32,6 +32,11 @@ template <typename T>
 int fv_tp2d_gated(int ni, int nj, int nk, int nb, F3<const T> q, F3<const T> crx, F3<const T> xfx, F3<const T> cry,
                   F3<const T> yfx, F2<const T> rarea, int* gate, F3<T> q_out, cudaStream_t s);
 
+// halo update of q + fv_tp2d in one launch; ctx / plan from b2s_halo_init / b2s_halo_plan (csrc/halo_ctx.cu)
+template <typename T>
+int halo_fv_tp2d(int64_t ctx, int plan, int ni, int nj, int nk, int nb, F3<const T> crx, F3<const T> xfx, F3<const T> cry,
+                 F3<const T> yfx, F2<const T> rarea, F3<T> q, F3<T> q_out, cudaStream_t s);
+
 template <typename T>
 int fv_tp2d_split(int ni, int nj, int nk, int nb, F3<const T> q, F3<const T> crx, F3<const T> xfx, F3<const T> cry,
                   F3<const T> yfx, F2<const T> area, F2<const T> rarea, const int* corner_flags, F3<T> q_out,

@@ -16,6 +16,7 @@
 // Same formulas, same explicit-rounding arithmetic as the other variants: identical bits (tests assert it).
 // Algorithmic bytes/point: 40 R + 8 W + 8/nk; smem fill per point: (JB + 6) / JB of it.
 #include "fv_math.cuh"
+#include "halo_device.cuh"
 #include "impl.cuh"
 #include "tma.cuh"
 
@@ -41,54 +42,44 @@ struct STile {
   static constexpr int STAGE_BYTES = YFX_OFF + ru(RB * BY * (int)sizeof(T), 128);
   static constexpr int TX_BYTES = RB * (BQ + 2 * BX + 2 * BY) * (int)sizeof(T);
   static constexpr int BAR_OFF = NSTAGE * STAGE_BYTES;
-  static constexpr int SMEM_BYTES = BAR_OFF + 2 * NSTAGE * 8;
+  static constexpr int SCRATCH_OFF = BAR_OFF + 2 * NSTAGE * 8;  // one int for the fused exchange phase
+  static constexpr int SMEM_BYTES = SCRATCH_OFF + 16;
   static constexpr int THREADS = TI + 32;
   static_assert(BQ <= 256 && TI % 32 == 0 && TI % V == 0, "tile width");
 };
 
-// A rectangle of cells [i0, i1) x [j0, j1) cut into strips of TI columns x blocks of jb rows; its items are
-// [start, end) of the launch's item list, ordered (row block fastest, strip, k, b) inside the rectangle.
-struct StreamRect {
-  int i0, i1, j0, j1, nstrips, njblk, jb, start, end;
-};
-
 template <typename T>
 struct FvStreamParams {
-  int nk, nitems;
-  // ungated launch: one rectangle.  Gated launch (fv_tp2d_gated): rect[0] = cells at least a strip width from the
-  // west / east edges and three rows from the south / north edges (their stencil reads no halo cell), then the west
-  // and east strips at full height and the south and north caps; the producer acquires `gate` before the first load
-  // of item `first_gated`.
-  int nrect;
-  StreamRect rect[5];
-  int* gate;
-  int first_gated;
-  int c0_q, c0_crx, c0_xfx, c0_cry, c0_yfx;  // TMA coordinate of compute column 0 of each field
-  int sh_q, sh_crx, sh_xfx, sh_cry, sh_yfx;  // (c0 + i0) % V, the same for every rectangle: a box starts at the aligned column before
+  int nk, i0, i1, j0, j1;
+  int nstrips, njblk, jb, nitems;
+  int c_q, c_crx, c_xfx, c_cry, c_yfx;       // TMA coordinate of compute column i0 (tensor bases are 16-byte aligned)
+  int sh_q, sh_crx, sh_xfx, sh_cry, sh_yfx;  // c % V: the box starts at the aligned column before
   F2<const T> rarea;
   F3<T> qout;
+  // gated launch (fv_tp2d_gated): gate[b] is raised by the halo exchange kernel when every halo cell of sub-domain b
+  // has landed; the producer acquires it before the first load of an item of that sub-domain.  nullptr: not gated.
+  int* gate;
+  // fused step (b2s_halo_fv_tp2d): x.links != nullptr -> every CTA first takes its share of the halo exchange
+  // (halo_device.cuh), then walks its stencil items behind the gates; halo update + transport are ONE launch
+  HaloXchg x;
+  int nb;
 };
 
 struct StreamItem {
-  int is, i1, jb0, nrows, k, b, nchunk;  // first column of the strip, end of the rectangle, first row, rows, level, sub-domain
+  int strip, jb0, nrows, k, b, nchunk;
 };
 
 template <typename T>
-__device__ __forceinline__ StreamItem stream_item(int item, const FvStreamParams<T>& P, int TI) {
-  int r = 0;
-  while (r + 1 < P.nrect && item >= P.rect[r].end) ++r;
-  const StreamRect& R = P.rect[r];
+__device__ __forceinline__ StreamItem stream_item(int item, const FvStreamParams<T>& P) {
   StreamItem it;
-  int t = item - R.start;
-  const int jblk = t % R.njblk;
-  t /= R.njblk;
-  it.is = R.i0 + (t % R.nstrips) * TI;
-  it.i1 = R.i1;
-  t /= R.nstrips;
+  const int jblk = item % P.njblk;
+  int t = item / P.njblk;
+  it.strip = t % P.nstrips;
+  t /= P.nstrips;
   it.k = t % P.nk;
   it.b = t / P.nk;
-  it.jb0 = R.j0 + jblk * R.jb;
-  it.nrows = min(R.jb, R.j1 - it.jb0);
+  it.jb0 = P.j0 + jblk * P.jb;
+  it.nrows = min(P.jb, P.j1 - it.jb0);
   it.nchunk = (it.nrows + 6 + RB - 1) / RB;
   return it;
 }
@@ -117,6 +108,7 @@ __global__ void __launch_bounds__(TI + 32) k_fv_stream(const __grid_constant__ C
     fence_barrier_init();
   }
   __syncthreads();
+  if (P.x.links != nullptr) halo_exchange_body<T>(P.x, reinterpret_cast<int*>(smem + G::SCRATCH_OFF));
 
   if (warp == NCONS_WARPS) {
     // =============================== PRODUCER ===============================
@@ -128,13 +120,14 @@ __global__ void __launch_bounds__(TI + 32) k_fv_stream(const __grid_constant__ C
       tma_prefetch_desc(&tm_yfx);
       int stage = 0;
       uint32_t phase = 0;
-      bool gate_open = P.gate == nullptr;
+      int b_open = P.gate == nullptr ? P.nb : 0;  // sub-domains below b_open have their halos (items run in b order)
       for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
-        const StreamItem it = stream_item(item, P, TI);
-        const int io = it.is;
-        if (!gate_open && item >= P.first_gated) {
-          gate_acquire(P.gate);  // the halo cells this item reads have landed (k_halo_exchange)
-          gate_open = true;
+        const StreamItem it = stream_item(item, P);
+        const int io = it.strip * TI;
+        while (b_open <= it.b) {
+          if (blockIdx.x == 0 && b_open == 0) gate_trace(P.gate, 3);
+          gate_acquire(P.gate, b_open++);
+          if (blockIdx.x == 0 && b_open == 1) gate_trace(P.gate, 4);
         }
         for (int m = 0; m < it.nchunk; ++m) {
           // chunk row rr of chunk m is iteration n = m*RB + rr: q row r = jb0 - 3 + n (tensor row r + 3: the map is
@@ -143,11 +136,11 @@ __global__ void __launch_bounds__(TI + 32) k_fv_stream(const __grid_constant__ C
           mbar_wait(&empty[stage], phase ^ 1);
           unsigned char* st = smem + stage * G::STAGE_BYTES;
           mbar_arrive_expect_tx(&full[stage], G::TX_BYTES);
-          tma_load_4d(st + G::Q_OFF, &tm_q, &full[stage], P.c0_q - P.sh_q + io, row, it.k, it.b);
-          tma_load_4d(st + G::CRX_OFF, &tm_crx, &full[stage], P.c0_crx - P.sh_crx + io, row - 3, it.k, it.b);
-          tma_load_4d(st + G::XFX_OFF, &tm_xfx, &full[stage], P.c0_xfx - P.sh_xfx + io, row - 3, it.k, it.b);
-          tma_load_4d(st + G::CRY_OFF, &tm_cry, &full[stage], P.c0_cry - P.sh_cry + io, row - 5, it.k, it.b);
-          tma_load_4d(st + G::YFX_OFF, &tm_yfx, &full[stage], P.c0_yfx - P.sh_yfx + io, row - 5, it.k, it.b);
+          tma_load_4d(st + G::Q_OFF, &tm_q, &full[stage], P.c_q - P.sh_q + io, row, it.k, it.b);
+          tma_load_4d(st + G::CRX_OFF, &tm_crx, &full[stage], P.c_crx - P.sh_crx + io, row - 3, it.k, it.b);
+          tma_load_4d(st + G::XFX_OFF, &tm_xfx, &full[stage], P.c_xfx - P.sh_xfx + io, row - 3, it.k, it.b);
+          tma_load_4d(st + G::CRY_OFF, &tm_cry, &full[stage], P.c_cry - P.sh_cry + io, row - 5, it.k, it.b);
+          tma_load_4d(st + G::YFX_OFF, &tm_yfx, &full[stage], P.c_yfx - P.sh_yfx + io, row - 5, it.k, it.b);
           if (++stage == NSTAGE) {
             stage = 0;
             phase ^= 1;
@@ -169,9 +162,9 @@ __global__ void __launch_bounds__(TI + 32) k_fv_stream(const __grid_constant__ C
   int stage = 0;
   uint32_t phase = 0;
   for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
-    const StreamItem it = stream_item(item, P, TI);
-    const int i = it.is + ci;
-    const bool col_ok = i < it.i1;
+    const StreamItem it = stream_item(item, P);
+    const int i = P.i0 + it.strip * TI + ci;
+    const bool col_ok = i < P.i1;
     const int nrows = it.nrows;
     // running pointers of the row stored at iteration n (row jb0 - 6 + n); dereferenced for 6 <= n < 6 + nrows only
     T* outp = P.qout.at(i, it.jb0 - 6, it.k, it.b);
@@ -232,13 +225,13 @@ __global__ void __launch_bounds__(TI + 32) k_fv_stream(const __grid_constant__ C
       for (int u = 0; u < RB; ++u) ra_cur[u] = ra_nxt[u];
     }
   }
-  if (P.gate != nullptr && threadIdx.x == 0) gate_release(P.gate, gridDim.x);  // this CTA's loads are all done
+  if (P.gate != nullptr && threadIdx.x == 0) gate_release(P.gate, P.nb, gridDim.x);  // this CTA has consumed all its loads
 }
 
 template <typename T, int TI, int NSTAGE>
 int launch_stream(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j1, F3<const T> q, F3<const T> crx,
                   F3<const T> xfx, F3<const T> cry, F3<const T> yfx, F2<const T> rarea, F3<T> q_out, cudaStream_t s,
-                  bool* applicable, int* gate) {
+                  bool* applicable, int* gate, const HaloXchg* xchg) {
   using G = STile<T, TI, NSTAGE>;
   constexpr int V = G::V;
   *applicable = false;
@@ -266,8 +259,8 @@ int launch_stream(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j1
     ctas_per_sm = nblk;
   }
   FvStreamParams<T> P;
-  P.nk = nk;
-  P.gate = gate;
+  P.nk = nk, P.i0 = i0, P.i1 = i1, P.j0 = j0, P.j1 = j1;
+  P.nstrips = (i1 - i0 + TI - 1) / TI;
   // Rows per item and grid size.  Items are long (a whole column height where possible) and the persistent grid
   // hands them out statically, so the split must come out even: for 1 .. 16 row blocks per column, model the
   // busiest SM (waves of items per CTA x CTAs on that SM) and keep the best of
@@ -278,7 +271,6 @@ int launch_stream(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j1
   // block per column = 1.46 items per CTA, 271 us; two blocks 254 us; three 279 us).
   // b2s_set_option("fv_jb", n) overrides the choice.
   const int h = j1 - j0;
-  const int nstrips = (i1 - i0 + TI - 1) / TI;
   const int64_t max_ctas = (int64_t)sm_count() * ctas_per_sm;
   auto even_grid = [&](int64_t n) { const int64_t waves = (n + max_ctas - 1) / max_ctas; return (n + waves - 1) / waves; };
   int jb = option("fv_jb", 0);
@@ -286,64 +278,30 @@ int launch_stream(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j1
     double best = -1.0;
     for (int nb_j = 1; nb_j <= 16 && (nb_j == 1 || h / nb_j >= 32); ++nb_j) {
       const int cand = (h + nb_j - 1) / nb_j;
-      const int64_t n = (int64_t)nstrips * ((h + cand - 1) / cand) * nk * nb;
+      const int64_t n = (int64_t)P.nstrips * ((h + cand - 1) / cand) * nk * nb;
       const int64_t waves = (n + max_ctas - 1) / max_ctas, g = even_grid(n);
       const int64_t busiest = (g + sm_count() - 1) / sm_count() * waves;
       const double score = (double)n / ((double)sm_count() * busiest) * cand / (cand + 42.0);
       if (score > best) best = score, jb = cand;
     }
   }
-  const int nblk_j = (h + jb - 1) / jb;  // row blocks of a full-height column
-  P.nrect = 0;
-  int64_t total = 0;
-  auto add_rect = [&](int ri0, int ri1, int rj0, int rj1, int blocks) {
-    if (ri1 <= ri0 || rj1 <= rj0) return;
-    StreamRect& r = P.rect[P.nrect];
-    r.i0 = ri0, r.i1 = ri1, r.j0 = rj0, r.j1 = rj1;
-    r.nstrips = (ri1 - ri0 + TI - 1) / TI;
-    const int rh = rj1 - rj0;
-    blocks = blocks < 1 ? 1 : (blocks > rh ? rh : blocks);
-    r.jb = (rh + blocks - 1) / blocks;
-    r.njblk = (rh + r.jb - 1) / r.jb;
-    r.start = (int)total;
-    total += (int64_t)r.nstrips * r.njblk * nk * nb;
-    r.end = (int)total;
-    ++P.nrect;
-  };
-  // strips (on the grid i0 + s * TI, so every box keeps the same alignment shift) whose x-apron reads no halo column
-  int s_lo = 0, s_hi = nstrips;
-  if (gate != nullptr) {
-    while (s_lo < nstrips && i0 + s_lo * TI < 3) ++s_lo;
-    while (s_hi > s_lo && (i0 + s_hi * TI < i1 ? i0 + s_hi * TI : i1) + 3 > ni) --s_hi;
-  }
-  const int jlo = j0 < 3 ? 3 : j0, jhi = j1 > nj - 3 ? nj - 3 : j1;  // rows whose stencil reads no halo row
-  int64_t n_long = 0;
-  if (gate == nullptr || s_lo >= s_hi || jlo >= jhi) {
-    add_rect(i0, i1, j0, j1, nblk_j);
-    P.first_gated = gate ? 0 : 1 << 30;
-    n_long = total;
-  } else {
-    const int xi0 = i0 + s_lo * TI, xi1 = i0 + s_hi * TI < i1 ? i0 + s_hi * TI : i1;
-    add_rect(xi0, xi1, jlo, jhi, nblk_j);  // interior first
-    P.first_gated = (int)total;
-    add_rect(i0, xi0, j0, j1, nblk_j);     // west strips, full height
-    add_rect(xi1, i1, j0, j1, nblk_j);     // east strips, full height
-    n_long = total;
-    add_rect(xi0, xi1, j0, jlo, 1);        // south cap
-    add_rect(xi0, xi1, jhi, j1, 1);        // north cap
-  }
-  if (total > (int64_t)1 << 30) return B2S_OK;
-  const int64_t nitems = total;
+  const int nblk_j = (h + jb - 1) / jb;
+  P.jb = (h + nblk_j - 1) / nblk_j;
+  P.njblk = (h + P.jb - 1) / P.jb;
+  const int64_t nitems = (int64_t)P.nstrips * P.njblk * nk * nb;
+  if (nitems > (int64_t)1 << 30) return B2S_OK;
   P.nitems = (int)nitems;
-  P.c0_q = fq.off, P.sh_q = (i0 + fq.off) % V;
-  P.c0_crx = fcx.off, P.sh_crx = (i0 + fcx.off) % V;
-  P.c0_xfx = fxx.off, P.sh_xfx = (i0 + fxx.off) % V;
-  P.c0_cry = fcy.off, P.sh_cry = (i0 + fcy.off) % V;
-  P.c0_yfx = fyx.off, P.sh_yfx = (i0 + fyx.off) % V;
+  P.c_q = i0 + fq.off, P.sh_q = P.c_q % V;
+  P.c_crx = i0 + fcx.off, P.sh_crx = P.c_crx % V;
+  P.c_xfx = i0 + fxx.off, P.sh_xfx = P.c_xfx % V;
+  P.c_cry = i0 + fcy.off, P.sh_cry = P.c_cry % V;
+  P.c_yfx = i0 + fyx.off, P.sh_yfx = P.c_yfx % V;
   P.rarea = rarea;
   P.qout = q_out;
-  // the grid is sized on the long items; the caps of a gated launch (three rows each) follow round-robin
-  const int grid = (int)even_grid(n_long);
+  P.gate = gate;
+  if (xchg != nullptr) P.x = *xchg; else P.x.links = nullptr;
+  P.nb = nb;
+  const int grid = (int)even_grid(nitems);
   *applicable = true;
   kern<<<grid, G::THREADS, G::SMEM_BYTES, s>>>(mq, mcx, mxx, mcy, myx, P);
   return check_launch("fv_tp2d(stream)");
@@ -351,12 +309,12 @@ int launch_stream(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j1
 
 }  // namespace
 
-#define B2S_FVS_ARGS ni, nj, nk, nb, i0, i1, j0, j1, q, crx, xfx, cry, yfx, rarea, q_out, s, applicable, gate
+#define B2S_FVS_ARGS ni, nj, nk, nb, i0, i1, j0, j1, q, crx, xfx, cry, yfx, rarea, q_out, s, applicable, gate, xchg
 
 template <typename T>
 int fv_tp2d_stream(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j1, F3<const T> q, F3<const T> crx,
                    F3<const T> xfx, F3<const T> cry, F3<const T> yfx, F2<const T> rarea, F3<T> q_out, cudaStream_t s,
-                   bool* applicable, int* gate) {
+                   bool* applicable, int* gate, const HaloXchg* xchg) {
   // strip width: the one of 128 / 96 / 64 columns that pads the rectangle least, the wider on ties (192-wide
   // sub-domains of the 8-GPU layout: two 96-column strips), 32 for narrow rectangles; ring depth
   // b2s_set_option("fv_stages", 2 | 3 | 4) for the 128- and 64-column kernels
@@ -382,10 +340,10 @@ int fv_tp2d_stream(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j
 
 template int fv_tp2d_stream<double>(int, int, int, int, int, int, int, int, F3<const double>, F3<const double>,
                                     F3<const double>, F3<const double>, F3<const double>, F2<const double>, F3<double>,
-                                    cudaStream_t, bool*, int*);
+                                    cudaStream_t, bool*, int*, const HaloXchg*);
 template int fv_tp2d_stream<float>(int, int, int, int, int, int, int, int, F3<const float>, F3<const float>,
                                    F3<const float>, F3<const float>, F3<const float>, F2<const float>, F3<float>,
-                                   cudaStream_t, bool*, int*);
+                                   cudaStream_t, bool*, int*, const HaloXchg*);
 
 }  // namespace impl
 }  // namespace b2s

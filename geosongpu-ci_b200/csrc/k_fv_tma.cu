@@ -19,6 +19,7 @@
 //     L2 hits because neighbouring tiles are consecutive in the item order.
 // Algorithmic bytes/point: 40 R + 8 W + 8/nk (same as variant 1).
 #include "fv_math.cuh"
+#include "halo_device.cuh"
 #include "impl.cuh"
 #include "tma.cuh"
 
@@ -52,34 +53,29 @@ struct Tile {
   static constexpr int STAGE_BYTES = YFX_OFF + round_up(Y_BYTES, 128);
   static constexpr int TX_BYTES = Q_BYTES + 2 * X_BYTES + 2 * Y_BYTES;
   static constexpr int BAR_OFF = NSTAGE * STAGE_BYTES;
-  static constexpr int SMEM_BYTES = BAR_OFF + 2 * NSTAGE * 8;
+  static constexpr int SCRATCH_OFF = BAR_OFF + 2 * NSTAGE * 8;  // one int for the fused exchange phase
+  static constexpr int SMEM_BYTES = SCRATCH_OFF + 16;
   static constexpr int THREADS = TI + 32;
   static_assert(BQ <= 256 && BX <= 256 && RQ <= 256, "TMA box dimensions are limited to 256 elements");
-};
-
-// A rectangle of tiles: strips [s0, s0 + ns) x row blocks [jb0, jb0 + nj) of every (k, b) level; its items are
-// [start, end) of the launch's item list, ordered (row block fastest, strip, k, b) inside the rectangle.
-struct TileRect {
-  int s0, ns, jb0, nj, start, end;
 };
 
 template <typename T>
 struct FvTmaParams {
   int nk, nb, i0, i1, j0, j1;
+  int nstrips, njblk;
   int nitems;
-  // ungated launch: one rectangle (all tiles).  Gated launch (fv_tp2d_gated): rect[0] = the tiles whose apron reads
-  // no halo cell, rect[1..] = the frame (south band, north band, west and east columns); the producer acquires
-  // `gate` before the first load of item `first_gated`.
-  int nrect;
-  TileRect rect[5];
-  int* gate;
-  int first_gated;
   // per field: c = TMA coordinate of compute column i0 (tensor base is 16-byte aligned), sh = c % V.
   // The box of a tile starts at c - sh + strip*TI; the tile's first needed element sits sh further.
   int c_q, c_crx, c_xfx, c_cry, c_yfx;
   int sh_q, sh_crx, sh_xfx, sh_cry, sh_yfx;
   F2<const T> rarea;
   F3<T> qout;
+  // gated launch (fv_tp2d_gated): gate[b] is raised by the halo exchange kernel when every halo cell of sub-domain b
+  // has landed; the producer acquires it before the first load of an item of that sub-domain.  nullptr: not gated.
+  int* gate;
+  // fused step (b2s_halo_fv_tp2d): x.links != nullptr -> every CTA first takes its share of the halo exchange
+  // (halo_device.cuh), then walks its stencil items behind the gates; halo update + transport are ONE launch
+  HaloXchg x;
 };
 
 // Position of a work item, advanced by gridDim.x items per step without divisions:
@@ -121,32 +117,6 @@ struct ItemCursor {
   }
 };
 
-// ItemCursor over a list of tile rectangles: the division-free advance inside a rectangle, a re-seek (a handful
-// of divisions) when the walk crosses into the next one -- at most nrect - 1 times per CTA.
-template <typename P>
-struct RectWalk {
-  int item, r;
-  ItemCursor cur;
-  __device__ __forceinline__ void seek(const P& p, int step) {
-    while (r + 1 < p.nrect && item >= p.rect[r].end) ++r;
-    cur.init(item - p.rect[r].start, step, p.rect[r].nj, p.rect[r].ns, p.nk);
-  }
-  __device__ __forceinline__ void init(const P& p, int first, int step) {
-    item = first, r = 0;
-    seek(p, step);
-  }
-  __device__ __forceinline__ void advance(const P& p, int step) {
-    item += step;
-    if (item >= p.rect[r].end) {
-      if (item < p.nitems) seek(p, step);
-    } else {
-      cur.advance(p.rect[r].nj, p.rect[r].ns, p.nk);
-    }
-  }
-  __device__ __forceinline__ int strip(const P& p) const { return p.rect[r].s0 + cur.strip; }
-  __device__ __forceinline__ int jb(const P& p) const { return p.rect[r].jb0 + cur.jb; }
-};
-
 template <typename T, int TI, int R, int NSTAGE>
 __global__ void __launch_bounds__(TI + 32) k_fv_tma(const __grid_constant__ CUtensorMap tm_q,
                                                     const __grid_constant__ CUtensorMap tm_crx,
@@ -175,9 +145,10 @@ __global__ void __launch_bounds__(TI + 32) k_fv_tma(const __grid_constant__ CUte
     fence_barrier_init();
   }
   __syncthreads();
+  if (P.x.links != nullptr) halo_exchange_body<T>(P.x, reinterpret_cast<int*>(smem + G::SCRATCH_OFF));
 
-  RectWalk<FvTmaParams<T>> cur;
-  cur.init(P, blockIdx.x, gridDim.x);
+  ItemCursor cur;
+  cur.init(blockIdx.x, gridDim.x, P.njblk, P.nstrips, P.nk);
   const int nmine = (P.nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp == NCONS_WARPS) {
@@ -190,25 +161,25 @@ __global__ void __launch_bounds__(TI + 32) k_fv_tma(const __grid_constant__ CUte
       tma_prefetch_desc(&tm_yfx);
       int stage = 0;
       uint32_t phase = 0;
-      bool gate_open = P.gate == nullptr;
+      int b_open = P.gate == nullptr ? P.nb : 0;  // sub-domains below b_open have their halos (items run in b order)
       for (int n = 0; n < nmine; ++n) {
-        const int io = cur.strip(P) * TI;     // column offset of the tile inside the rectangle
-        const int js = P.j0 + cur.jb(P) * R;  // first compute row of the tile
-        const int kk = cur.cur.k, bb = cur.cur.b;
-        if (!gate_open && cur.item >= P.first_gated) {
-          gate_acquire(P.gate);  // the halo cells this tile's apron reads have landed (k_halo_exchange)
-          gate_open = true;
+        const int io = cur.strip * TI;     // column offset of the tile inside the rectangle
+        const int js = P.j0 + cur.jb * R;  // first compute row of the tile
+        while (b_open <= cur.b) {
+          if (blockIdx.x == 0 && b_open == 0) gate_trace(P.gate, 3);
+          gate_acquire(P.gate, b_open++);
+          if (blockIdx.x == 0 && b_open == 1) gate_trace(P.gate, 4);
         }
         mbar_wait(&empty[stage], phase ^ 1);
         unsigned char* st = smem + stage * G::STAGE_BYTES;
         mbar_arrive_expect_tx(&full[stage], G::TX_BYTES);
         // q's tensor map is based at the halo origin (-3,-3): compute cell i-3 is coordinate i, row j-3 is row j
-        tma_load_4d(st + G::Q_OFF, &tm_q, &full[stage], P.c_q - P.sh_q + io, js, kk, bb);
-        tma_load_4d(st + G::CRX_OFF, &tm_crx, &full[stage], P.c_crx - P.sh_crx + io, js, kk, bb);
-        tma_load_4d(st + G::XFX_OFF, &tm_xfx, &full[stage], P.c_xfx - P.sh_xfx + io, js, kk, bb);
-        tma_load_4d(st + G::CRY_OFF, &tm_cry, &full[stage], P.c_cry - P.sh_cry + io, js, kk, bb);
-        tma_load_4d(st + G::YFX_OFF, &tm_yfx, &full[stage], P.c_yfx - P.sh_yfx + io, js, kk, bb);
-        cur.advance(P, gridDim.x);
+        tma_load_4d(st + G::Q_OFF, &tm_q, &full[stage], P.c_q - P.sh_q + io, js, cur.k, cur.b);
+        tma_load_4d(st + G::CRX_OFF, &tm_crx, &full[stage], P.c_crx - P.sh_crx + io, js, cur.k, cur.b);
+        tma_load_4d(st + G::XFX_OFF, &tm_xfx, &full[stage], P.c_xfx - P.sh_xfx + io, js, cur.k, cur.b);
+        tma_load_4d(st + G::CRY_OFF, &tm_cry, &full[stage], P.c_cry - P.sh_cry + io, js, cur.k, cur.b);
+        tma_load_4d(st + G::YFX_OFF, &tm_yfx, &full[stage], P.c_yfx - P.sh_yfx + io, js, cur.k, cur.b);
+        cur.advance(P.njblk, P.nstrips, P.nk);
         if (++stage == NSTAGE) {
           stage = 0;
           phase ^= 1;
@@ -229,12 +200,12 @@ __global__ void __launch_bounds__(TI + 32) k_fv_tma(const __grid_constant__ CUte
   int stage = 0;
   uint32_t phase = 0;
   for (int n = 0; n < nmine; ++n) {
-    const int i = P.i0 + cur.strip(P) * TI + ci;
-    const int js = P.j0 + cur.jb(P) * R;
+    const int i = P.i0 + cur.strip * TI + ci;
+    const int js = P.j0 + cur.jb * R;
     const int nrows = i < P.i1 ? min(R, P.j1 - js) : 0;  // rows of this tile this thread stores
-    const T* rap = P.rarea.at(i, js, cur.cur.b);
-    T* outp = P.qout.at(i, js, cur.cur.k, cur.cur.b);
-    cur.advance(P, gridDim.x);
+    const T* rap = P.rarea.at(i, js, cur.b);
+    T* outp = P.qout.at(i, js, cur.k, cur.b);
+    cur.advance(P.njblk, P.nstrips, P.nk);
 
     // rarea does not go through shared memory: R independent loads issued before the wait
     T ra[R];
@@ -289,7 +260,7 @@ __global__ void __launch_bounds__(TI + 32) k_fv_tma(const __grid_constant__ CUte
       phase ^= 1;
     }
   }
-  if (P.gate != nullptr && threadIdx.x == 0) gate_release(P.gate, gridDim.x);  // this CTA's loads are all done
+  if (P.gate != nullptr && threadIdx.x == 0) gate_release(P.gate, P.nb, gridDim.x);  // this CTA has consumed all its loads
 }
 
 // ---- host side (tensor maps: tma.cuh / tma_host.cu) ------------------------------------------------
@@ -297,7 +268,7 @@ __global__ void __launch_bounds__(TI + 32) k_fv_tma(const __grid_constant__ CUte
 template <typename T, int TI, int R, int NSTAGE>
 int launch(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j1, F3<const T> q, F3<const T> crx,
            F3<const T> xfx, F3<const T> cry, F3<const T> yfx, F2<const T> rarea, F3<T> q_out, cudaStream_t s,
-           bool* applicable, int* gate) {
+           bool* applicable, int* gate, const HaloXchg* xchg) {
   using G = Tile<T, TI, R, NSTAGE>;
   *applicable = false;
   // q's tensor starts at the halo origin (-3, -3)
@@ -333,40 +304,11 @@ int launch(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j1, F3<co
   P.i1 = i1;
   P.j0 = j0;
   P.j1 = j1;
-  const int nstrips = (i1 - i0 + TI - 1) / TI;
-  const int njblk = (j1 - j0 + R - 1) / R;
-  const int64_t nitems = (int64_t)nstrips * njblk * nk * nb;
+  P.nstrips = (i1 - i0 + TI - 1) / TI;
+  P.njblk = (j1 - j0 + R - 1) / R;
+  const int64_t nitems = (int64_t)P.nstrips * P.njblk * nk * nb;
   if (nitems > (int64_t)1 << 30) return B2S_OK;  // beyond the 32-bit item cursor: direct kernel
   P.nitems = (int)nitems;
-  P.gate = gate;
-  P.nrect = 0;
-  auto add_rect = [&](int s0, int s1, int jb0, int jb1) {
-    if (s1 <= s0 || jb1 <= jb0) return;
-    TileRect& r = P.rect[P.nrect];
-    r.s0 = s0, r.ns = s1 - s0, r.jb0 = jb0, r.nj = jb1 - jb0;
-    r.start = P.nrect ? P.rect[P.nrect - 1].end : 0;
-    r.end = r.start + r.ns * r.nj * nk * nb;
-    ++P.nrect;
-  };
-  // tiles whose apron stays inside the compute domain: strips [s_lo, s_hi) x row blocks [jb_lo, jb_hi)
-  int s_lo = 0, s_hi = nstrips, jb_lo = 0, jb_hi = njblk;
-  if (gate != nullptr) {
-    while (s_lo < nstrips && i0 + s_lo * TI < 3) ++s_lo;
-    while (s_hi > s_lo && i0 + (s_hi * TI < i1 - i0 ? s_hi * TI : i1 - i0) + 3 > ni) --s_hi;
-    while (jb_lo < njblk && j0 + jb_lo * R < 3) ++jb_lo;
-    while (jb_hi > jb_lo && j0 + (jb_hi * R < j1 - j0 ? jb_hi * R : j1 - j0) + 3 > nj) --jb_hi;
-  }
-  if (gate == nullptr || s_lo >= s_hi || jb_lo >= jb_hi) {
-    add_rect(0, nstrips, 0, njblk);
-    P.first_gated = gate ? 0 : P.nitems;
-  } else {
-    add_rect(s_lo, s_hi, jb_lo, jb_hi);  // interior first
-    P.first_gated = P.rect[0].end;
-    add_rect(0, nstrips, 0, jb_lo);        // south band
-    add_rect(0, nstrips, jb_hi, njblk);    // north band
-    add_rect(0, s_lo, jb_lo, jb_hi);       // west columns
-    add_rect(s_hi, nstrips, jb_lo, jb_hi); // east columns
-  }
   constexpr int V = G::V;
   static_assert(TI % V == 0, "tile width must keep the box start alignment from strip to strip");
   P.c_q = i0 + fq.off, P.sh_q = P.c_q % V;
@@ -376,6 +318,8 @@ int launch(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j1, F3<co
   P.c_yfx = i0 + fyx.off, P.sh_yfx = P.c_yfx % V;
   P.rarea = rarea;
   P.qout = q_out;
+  P.gate = gate;
+  if (xchg != nullptr) P.x = *xchg; else P.x.links = nullptr;
   const int64_t max_ctas = (int64_t)sm_count() * ctas_per_sm;
   const int grid = (int)(nitems < max_ctas ? nitems : max_ctas);
   *applicable = true;
@@ -385,12 +329,12 @@ int launch(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j1, F3<co
 
 }  // namespace
 
-#define B2S_FV_ARGS ni, nj, nk, nb, i0, i1, j0, j1, q, crx, xfx, cry, yfx, rarea, q_out, s, applicable, gate
+#define B2S_FV_ARGS ni, nj, nk, nb, i0, i1, j0, j1, q, crx, xfx, cry, yfx, rarea, q_out, s, applicable, gate, xchg
 
 template <typename T, int TI>
 int launch_rows_stages(int rows, int stages, int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j1,
                        F3<const T> q, F3<const T> crx, F3<const T> xfx, F3<const T> cry, F3<const T> yfx,
-                       F2<const T> rarea, F3<T> q_out, cudaStream_t s, bool* applicable, int* gate) {
+                       F2<const T> rarea, F3<T> q_out, cudaStream_t s, bool* applicable, int* gate, const HaloXchg* xchg) {
   if (rows == 8) return stages == 3 ? launch<T, TI, 8, 3>(B2S_FV_ARGS) : launch<T, TI, 8, 2>(B2S_FV_ARGS);
   return stages == 3 ? launch<T, TI, 4, 3>(B2S_FV_ARGS) : launch<T, TI, 4, 2>(B2S_FV_ARGS);
 }
@@ -398,7 +342,7 @@ int launch_rows_stages(int rows, int stages, int ni, int nj, int nk, int nb, int
 template <typename T>
 int fv_tp2d_tma(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j1, F3<const T> q, F3<const T> crx,
                 F3<const T> xfx, F3<const T> cry, F3<const T> yfx, F2<const T> rarea, F3<T> q_out, cudaStream_t s,
-                bool* applicable, int* gate) {
+                bool* applicable, int* gate, const HaloXchg* xchg) {
   // Tile geometry.  Width TI = consumer threads per CTA (+ 1 producer warp); widths on offer: 32
   // (narrow boundary strips), 64, 96, 128, 192 columns; R rows per stage; NSTAGE-deep ring.
   // Automatic choice, from the sweeps in profiles/r01_fv_tile_sweep.md:
@@ -450,10 +394,10 @@ int fv_tp2d_tma(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j1, 
 
 template int fv_tp2d_tma<double>(int, int, int, int, int, int, int, int, F3<const double>, F3<const double>,
                                  F3<const double>, F3<const double>, F3<const double>, F2<const double>,
-                                 F3<double>, cudaStream_t, bool*, int*);
+                                 F3<double>, cudaStream_t, bool*, int*, const HaloXchg*);
 template int fv_tp2d_tma<float>(int, int, int, int, int, int, int, int, F3<const float>, F3<const float>,
                                 F3<const float>, F3<const float>, F3<const float>, F2<const float>, F3<float>,
-                                cudaStream_t, bool*, int*);
+                                cudaStream_t, bool*, int*, const HaloXchg*);
 
 }  // namespace impl
 }  // namespace b2s

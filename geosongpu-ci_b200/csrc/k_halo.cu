@@ -8,6 +8,7 @@
 // Negative strides express the index reversal / rotation across cubed-sphere tile edges.
 //   pack:   src = field, dst = send buffer      unpack: src = recv buffer, dst = field
 //   local:  src = dst = field (neighbouring sub-domains resident on the same GPU)
+#include "halo_device.cuh"
 #include "impl.cuh"
 
 namespace b2s {
@@ -45,16 +46,6 @@ __device__ __forceinline__ void copy_levels(const T* sp, int64_t ssk, T* dp, int
 static int halo_levels() {
   const int ku = option("halo_levels", kKU);
   return ku == 4 || ku == 8 ? ku : kKU;
-}
-
-__device__ __forceinline__ void strip_decode(int t, int nd, int np, int64_t ssd, int& d, int& p) {
-  if (ssd == 1 || ssd == -1) {  // depth runs along i on the source side
-    d = t % nd;
-    p = t / nd;
-  } else {
-    p = t % np;
-    d = t / np;
-  }
 }
 
 template <typename T, int KU>
@@ -136,85 +127,37 @@ int halo_pull(int nlinks, int nk, int max_strip, const int64_t* links, T* dst, c
 //     rank r's array as mapped into this process;
 //   * the step number (epoch) lives on the device (state[0]), so a CUDA graph can replay the launch: every block
 //     reads it at entry, the last block to finish advances it (state[1] counts blocks);
-//   * block (0,0,0) announces "my field is final for this epoch" to every peer: st.release.sys of the epoch into
+//   * block 0 announces "my field is final for this epoch" to every peer: st.release.sys of the epoch into
 //     flags[my_rank] of each peer (the field was written by earlier kernels in stream order);
-//   * a block whose link reads a peer waits (ld.acquire.sys on its OWN flag array, a local poll) until that peer's
+//   * a block whose next strip reads a peer waits (ld.acquire.sys on its OWN flag array, a local poll) until that peer's
 //     announcement has arrived, then pulls.  Announcements are monotonic, a rank can run at most one step ahead of
 //     a neighbour, and -- adjacency being symmetric -- a neighbour's announcement of epoch n+1 also says it has
 //     finished pulling epoch n from this rank, which is what a ping-pong time loop needs before overwriting;
-//   * gated: the last block raises state[8] (the gate, st.release.gpu) once every halo cell has been written;
-//     gated stencil kernels acquire it before their first load of a halo cell and lower it when they finish;
+//   * gated: links are sorted by destination sub-domain b and carry it in word [11]; the last block of the links
+//     into sub-domain b raises gate[b] (st.release.gpu) -- blocks are dispatched in link order, so the gates open
+//     one sub-domain after the other.  A gated stencil (fv_tp2d_gated) walks its items in the same order, acquires
+//     gate[b] before its first load of sub-domain b and lowers the gates when it finishes: the exchange of
+//     sub-domains 1.. overlaps the stencil of sub-domains 0.., with the stencil's DRAM-friendly item order untouched
+//     (an interior-cells-first order was measured and costs 13-28 % of the stencil: profiles/r02_overlap.md);
 //   * no wait is unbounded: after ~2 s of spinning a block records status 1 in state[2] and carries on
 //     (wrong halos, reported by b2s_halo_status, instead of a hung GPU).
-// Link words: 0..9 as halo_move, [10] base address of the source buffer, [11] owning rank (-1: this GPU).
+// Link words: 0..9 as halo_move, [10] base address of the source buffer, [11] = (owning rank + 1) | (b << 16) with
+// owning rank -1 for this GPU and b the destination sub-domain (batch index).
+// state: [0] epoch, [1] blocks done, [2] status, [kDoneWord + b] blocks done for sub-domain b, [kGateWord + b] gate b.
 // -------------------------------------------------------------------------------------------
-static constexpr int kExchangeWords = 12;
-static constexpr long long kSyncTimeoutCycles = 4000000000LL;
-static constexpr int kGateWord = 8;
-
-__device__ __forceinline__ void st_release_sys(int* p, int v) { asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ void st_release_gpu(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ int ld_acquire_sys(const int* p) {
-  int v;
-  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
+// PERSISTENT grid: gridDim.x = a few blocks per SM walk the (link, level) work units in link order.  A
+// one-block-per-strip grid was measured first: thousands of 256-thread blocks fill every thread slot of the GPU, a
+// stencil launched beside them cannot become resident until they drain, and the "overlapped" step was as long as the
+// serial one (profiles/r02_overlap.md).  The body lives in halo_device.cuh: the fused step (b2s_halo_fv_tp2d) runs
+// it as the first phase of the stencil kernel instead.
 template <typename T>
-__global__ void __launch_bounds__(256) k_halo_exchange(int nk, const int64_t* __restrict__ links, T* dst, int my_rank, int world,
-                                                       const int64_t* __restrict__ peer_flags, int* state, int gated) {
+__global__ void __launch_bounds__(256) k_halo_exchange(const HaloXchg X) {
   __shared__ int s_epoch;
-  if (threadIdx.x == 0) s_epoch = *reinterpret_cast<volatile int*>(state) + 1;
-  __syncthreads();
-  const int epoch = s_epoch;
-  if (world > 1 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (int)threadIdx.x < world && (int)threadIdx.x != my_rank) {
-    __threadfence_system();
-    st_release_sys(reinterpret_cast<int*>(static_cast<uintptr_t>(peer_flags[threadIdx.x])) + my_rank, epoch);
-  }
-
-  const int64_t* L = links + (int64_t)blockIdx.z * kExchangeWords;
-  const int src_rank = (int)L[11];
-  if (src_rank >= 0 && src_rank != my_rank) {
-    if (threadIdx.x == 0) {
-      const int* mine = reinterpret_cast<const int*>(static_cast<uintptr_t>(peer_flags[my_rank])) + src_rank;
-      const long long t0 = clock64();
-      while (ld_acquire_sys(mine) < epoch) {
-        if (clock64() - t0 > kSyncTimeoutCycles) {
-          atomicExch(state + 2, 1);
-          break;
-        }
-      }
-    }
-    __syncthreads();
-  }
-
-  const int nd = (int)L[8], np = (int)L[9];
-  const int t = blockIdx.x * 256 + threadIdx.x;
-  if (t < nd * np) {
-    const T* src = reinterpret_cast<const T*>(static_cast<uintptr_t>(L[10]));
-    const int64_t ssd = L[1], ssp = L[2], ssk = L[3], dsk = L[7];
-    int d, p;
-    strip_decode(t, nd, np, ssd, d, p);
-    const int k0 = blockIdx.y;
-    dst[L[4] + d * L[5] + p * L[6] + k0 * dsk] = src[L[0] + d * ssd + p * ssp + k0 * ssk];
-  }
-
-  // the last block to finish publishes the halos (gate) and advances the epoch for the next launch / graph replay
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const int total = (int)(gridDim.x * gridDim.y * gridDim.z);
-    if (atomicAdd(state + 1, 1) == total - 1) {
-      state[1] = 0;
-      __threadfence();
-      *reinterpret_cast<volatile int*>(state) = epoch;
-      if (gated) st_release_gpu(state + kGateWord, 1);
-    }
-  }
+  halo_exchange_body<T>(X, &s_epoch);
 }
 
 // an exchange without links still has to announce, advance the epoch and raise the gate
-__global__ void k_halo_exchange_empty(int my_rank, int world, const int64_t* __restrict__ peer_flags, int* state, int gated) {
+__global__ void k_halo_exchange_empty(int my_rank, int world, const int64_t* __restrict__ peer_flags, int* state, int nb, int gated) {
   const int epoch = *reinterpret_cast<volatile int*>(state) + 1;
   if ((int)threadIdx.x < world && (int)threadIdx.x != my_rank) {
     __threadfence_system();
@@ -223,24 +166,27 @@ __global__ void k_halo_exchange_empty(int my_rank, int world, const int64_t* __r
   __syncthreads();
   if (threadIdx.x == 0) {
     *reinterpret_cast<volatile int*>(state) = epoch;
-    if (gated) st_release_gpu(state + kGateWord, 1);
+    if (gated)
+      for (int b = 0; b < nb; ++b) st_release_gpu(state + kGateWord + b, 1);
   }
 }
 
-int halo_exchange_launch(int elem_size, int nlinks, int nk, int max_strip, int my_rank, int world, const int64_t* links,
-                         const int64_t* peer_flags, int* state, void* dst, int gated, cudaStream_t s) {
-  B2S_ARGCHECK(world >= 1 && world <= 64 && my_rank >= 0 && my_rank < world, "halo_exchange: rank %d of %d", my_rank, world);
-  B2S_ARGCHECK(peer_flags && state, "halo_exchange: null pointer");
-  if (nlinks == 0) {
-    k_halo_exchange_empty<<<1, 64, 0, s>>>(my_rank, world, peer_flags, state, gated);
+int halo_exchange_launch(int elem_size, int nb, const HaloXchg& X, cudaStream_t s) {
+  B2S_ARGCHECK(X.world >= 1 && X.world <= 64 && X.my_rank >= 0 && X.my_rank < X.world, "halo_exchange: rank %d of %d", X.my_rank, X.world);
+  B2S_ARGCHECK(X.peer_flags && X.state, "halo_exchange: null pointer");
+  if (X.nlinks == 0) {
+    k_halo_exchange_empty<<<1, 64, 0, s>>>(X.my_rank, X.world, X.peer_flags, X.state, nb, X.gated);
     return check_launch("halo_exchange");
   }
-  B2S_ARGCHECK(nk > 0 && max_strip > 0 && links && dst, "halo_exchange: bad sizes nlinks=%d nk=%d max_strip=%d", nlinks, nk, max_strip);
-  dim3 grid((max_strip + 255) / 256, nk, nlinks);
+  B2S_ARGCHECK(X.nk > 0 && X.links && X.dst && X.b_total, "halo_exchange: bad sizes nlinks=%d nk=%d", X.nlinks, X.nk);
+  int per_sm = option("halo_blocks_per_sm", 0);
+  if (per_sm <= 0 || per_sm > 8) per_sm = 2;  // 2 x 256 threads x 54 registers leave room for four stencil CTAs per SM
+  const int64_t units = (int64_t)X.nlinks * X.nk;
+  const int grid = (int)(units < (int64_t)sm_count() * per_sm ? units : (int64_t)sm_count() * per_sm);
   if (elem_size == 8)
-    k_halo_exchange<double><<<grid, 256, 0, s>>>(nk, links, static_cast<double*>(dst), my_rank, world, peer_flags, state, gated);
+    k_halo_exchange<double><<<grid, 256, 0, s>>>(X);
   else
-    k_halo_exchange<float><<<grid, 256, 0, s>>>(nk, links, static_cast<float*>(dst), my_rank, world, peer_flags, state, gated);
+    k_halo_exchange<float><<<grid, 256, 0, s>>>(X);
   return check_launch("halo_exchange");
 }
 

@@ -47,32 +47,48 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 }
 
 // ---- halo gate (csrc/halo_ctx.cu, k_halo.cu k_halo_exchange) -----------------------------------
-// gate[0]: raised (st.release.gpu) by the exchange kernel when every halo cell has been written; gate[1]: CTAs of the
-// consuming stencil that have issued all their loads; gate[2]: status (1 = a wait gave up).  The producer lane of a
-// gated stencil acquires gate[0] before its first TMA load that touches a halo cell; the cells were written through
-// the generic proxy by another kernel and are read through the async proxy, hence the proxy fence.  Bounded spin: a
-// protocol error becomes a status word (b2s_halo_status), not a hung GPU.
-__device__ __forceinline__ void gate_acquire(int* gate) {
+// gate[b], b < kGateSlots: raised (st.release.gpu) by the exchange kernel when every halo cell of sub-domain b has
+// been written; gate[kGateSlots]: CTAs of the consuming stencil that have finished; gate[kGateSlots + 1]: status
+// (1 = a wait gave up).  A gated stencil walks its items in sub-domain order; its producer lane acquires gate[b]
+// before the first TMA load of sub-domain b.  The halo cells were written through the generic proxy by another
+// kernel and are read through the async proxy, hence the proxy fence.  Bounded spin: a protocol error becomes a
+// status word (b2s_halo_status), not a hung GPU.
+static constexpr int kGateSlots = 64;
+static constexpr int kGateTraceOffset = 72;  // int offset from the gate words to the uint64 timeline slots (diagnostics)
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// timeline of the overlapped step, written by a handful of threads (b2s_halo_trace): [0] exchange start, [1] exchange
+// end, [2] gate 0 opened, [3] first stencil CTA started, [4] stencil CTA 0 got gate 0, [5] last stencil CTA finished
+__device__ __forceinline__ void gate_trace(int* gate, int slot) {
+  reinterpret_cast<unsigned long long*>(gate + kGateTraceOffset)[slot] = global_timer_ns();
+}
+
+__device__ __forceinline__ void gate_acquire(int* gate, int b) {
   int v;
   const long long t0 = clock64();
   for (;;) {
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(gate) : "memory");
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(gate + b) : "memory");
     if (v != 0) break;
     if (clock64() - t0 > 4000000000LL) {
-      atomicExch(gate + 2, 1);
+      atomicExch(gate + kGateSlots + 1, 1);
       break;
     }
     __nanosleep(64);
   }
   asm volatile("fence.proxy.async.global;" ::: "memory");
 }
-// called by one thread per CTA after the CTA's last load: the last CTA lowers the gate for the next exchange
-__device__ __forceinline__ void gate_release(int* gate, int nctas) {
+// called by one thread per CTA when the CTA is done: the last CTA lowers the gates for the next exchange
+__device__ __forceinline__ void gate_release(int* gate, int nb, int nctas) {
   __threadfence();
-  if (atomicAdd(gate + 1, 1) == nctas - 1) {
-    gate[1] = 0;
+  if (atomicAdd(gate + kGateSlots, 1) == nctas - 1) {
+    gate[kGateSlots] = 0;
+    for (int b = 0; b < nb; ++b) gate[b] = 0;
+    gate_trace(gate, 5);
     __threadfence();
-    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(gate), "r"(0) : "memory");
   }
 }
 

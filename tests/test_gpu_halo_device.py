@@ -5,8 +5,9 @@
 * the library-owned exchange (``b2s_halo_init / alloc / plan / exchange`` -- csrc/halo_ctx.cu, k_halo_exchange):
   one thread per virtual rank, the ranks meet in the shared-memory rendezvous and handshake through their flag
   arrays exactly as separate processes on separate GPUs do; three epochs exercise the device-resident step counter;
-* the gated stencil (``b2s_fv_tp2d_gated_c``): exchange forked onto the context's stream, halo-independent cells
-  first, the rest after the gate -- bit-identical to exchange-then-stencil, eagerly and under CUDA-graph replay.
+* the gated stencil (``b2s_fv_tp2d_gated_c``): exchange forked onto the context's stream, one gate per sub-domain,
+  sub-domain b computed while the halos of b+1.. arrive -- bit-identical to exchange-then-stencil, eagerly and
+  under CUDA-graph replay.
 
 Every halo cell is checked against the partitioner's geometric definition (global-id fields), edges and corners,
 for the 1/2/4/8-GPU decompositions (SURVEY.md 8e "every halo cell must hold the ID of its geometric neighbour").
@@ -153,11 +154,34 @@ def test_gated_step_equals_exchange_then_stencil(variant, N, nk, dtype):
             assert torch.equal(q[:, :, 3:-3], ref_q[:, :, 3:-3]) and torch.equal(q[:, 3:-3], ref_q[:, 3:-3]), "halos differ"
             assert torch.equal(out, ref), f"rep {rep}: max |diff| = {(out - ref).abs().max().item():.3e}"
         assert ctx.status() == (3, 0)
-        assert ctx.gate[:2].tolist() == [0, 0], "the gate must be lowered after every gated launch"
+        assert ctx.gate[:65].abs().sum().item() == 0, "the gates must be lowered after every gated launch"
         # serial device path
         out = F.zeros((N, N, nk), dtype, batch=6)
         FvTransport(part, 1, 0, exchange="device", halo_exchange=ex, overlap=False).step(q, d["crx"], d["xfx"], d["cry"], d["yfx"], d["rarea"], out)
         assert torch.equal(out, ref)
+        # fused: halo update + stencil in ONE launch (b2s_halo_fv_tp2d), eagerly and from a replayed graph
+        fz = FvTransport(part, 1, 0, exchange="device", halo_exchange=ex, fused=True)
+        for rep in range(2):
+            q[:, -3:] = -9.0  # scrub the east halo
+            out = F.zeros((N, N, nk), dtype, batch=6)
+            launches = _abi.launch_count()
+            fz.step(q, d["crx"], d["xfx"], d["cry"], d["yfx"], d["rarea"], out)
+            assert _abi.launch_count() - launches == 1, "the fused step is one kernel launch"
+            torch.cuda.synchronize()
+            assert torch.equal(q[:, :, 3:-3], ref_q[:, :, 3:-3]) and torch.equal(out, ref), f"fused rep {rep}"
+        capf = torch.cuda.Stream()
+        capf.wait_stream(torch.cuda.current_stream())
+        gf = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gf, stream=capf):
+            fz.step(q, d["crx"], d["xfx"], d["cry"], d["yfx"], d["rarea"], out)
+        for rep in range(2):
+            q[:, :3] = -7.0
+            out.zero_()
+            gf.replay()
+            torch.cuda.synchronize()
+            assert torch.equal(out, ref), f"fused graph replay {rep}"
+        del gf
+        assert ctx.gate[:65].abs().sum().item() == 0
         # CUDA graph: capture the forked step once, replay it
         out = F.zeros((N, N, nk), dtype, batch=6)
         tr.step(q, d["crx"], d["xfx"], d["cry"], d["yfx"], d["rarea"], out)  # marshal outside the capture
@@ -174,16 +198,18 @@ def test_gated_step_equals_exchange_then_stencil(variant, N, nk, dtype):
             assert torch.equal(out, ref), f"graph replay {rep}"
         del graph
         epoch, status = ctx.status()
-        assert status == 0 and epoch == 8
+        assert status == 0 and epoch == 12
     finally:
         _abi.set_option("fv_variant", 0)
         ctx.finalize()
 
 
+@pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("n_gpus", [2, 8])
-def test_gated_step_virtual_ranks(n_gpus):
-    """Handshake + pull + gate together: every virtual rank runs overlapped transport steps; results equal the
-    exchange-in-process reference (CUDA halo_move tables) followed by the plain stencil."""
+def test_gated_step_virtual_ranks(n_gpus, fused):
+    """Handshake + pull + gate together: every virtual rank runs overlapped (forked exchange beside the gated stencil)
+    or fused (ONE kernel per step) transport steps; results equal the exchange-in-process reference (CUDA halo_move
+    tables) followed by the plain stencil.  The domains are small, so all the ranks' grids are co-resident on the GPU."""
     from b200stencil.halo.updater import exchange_in_process
 
     N, nk, dtype = 48, 2, torch.float64
@@ -211,7 +237,7 @@ def test_gated_step_virtual_ranks(n_gpus):
             q = ctx.field((ni + 6, nj + 6, nk), nsub, dtype)
             q[:, 3:-3, 3:-3] = data[rank]["core"]
             ex = ctx.plan(q, part)
-            tr = FvTransport(part, n_gpus, rank, exchange="device", halo_exchange=ex, overlap=True)
+            tr = FvTransport(part, n_gpus, rank, exchange="device", halo_exchange=ex, overlap=True, fused=fused)
             d = data[rank]
             torch.cuda.current_stream().synchronize()
             ctx.barrier()

@@ -722,9 +722,23 @@ def test_error_channel(st):
     with pytest.raises(TypeError):
         st.top_of_column(I, up(np.zeros((4, 4), np.float32)), I)  # dtype mismatch: no casting
     q = up(np.zeros((10, 10, 2)))
-    with pytest.raises(_abi.B200StencilError) as e:
-        st.fv_tp2d(q, q, q, q, q, up(np.zeros((4, 4))), up(np.zeros((4, 4, 2))), region=(0, 9, 0, 4))
+    cx, cy = up(np.zeros((5, 4, 2))), up(np.zeros((4, 5, 2)))
+    with pytest.raises(_abi.B200StencilError) as e:  # the library's own check: the C side refuses the rectangle
+        st.fv_tp2d(q, cx, cx, cy, cy, up(np.zeros((4, 4))), up(np.zeros((4, 4, 2))), region=(0, 9, 0, 4))
     assert "rectangle" in str(e.value)
+    # the C-ABI carries no extents with a pointer: a wrongly shaped field must be refused on the host side
+    with pytest.raises(ValueError, match="crx has shape"):
+        st.fv_tp2d(q, q, cx, cy, cy, up(np.zeros((4, 4))), up(np.zeros((4, 4, 2))))
+    with pytest.raises(ValueError, match="q_out has shape"):
+        st.fv_tp2d(q, cx, cx, cy, cy, up(np.zeros((4, 4))), up(np.zeros((4, 5, 2))))
+    with pytest.raises(ValueError, match="PLEmb_top has shape"):
+        st.top_of_column(I, up(np.zeros((4, 5))), I)
+    with pytest.raises(ValueError, match="pe has shape"):
+        st.pe_prefix(I, 1.0, up(np.zeros((4, 4, 4))))  # nk + 1 interface levels wanted
+    with pytest.raises(ValueError, match="pe2 has shape"):
+        st.remap(up(np.zeros((4, 4, 5))), I, up(np.zeros((4, 4, 4))), up(np.zeros((4, 4, 2))))  # q2 has 2 layers: pe2 needs 3 edges
+    with pytest.raises(ValueError, match="ktop has shape"):
+        st.cloud_top(I, torch.zeros((4, 3), dtype=torch.int64, device="cuda"))
     bad = torch.zeros((4, 4, 4), dtype=torch.float64, device="cuda")  # k-fastest: rejected
     with pytest.raises(ValueError):
         st.top_of_column(bad, up(np.zeros((4, 4))), I)

@@ -200,7 +200,7 @@ def test_halo_exchange_gloo(world):
 
 def test_plan_tables_name_the_owner_of_every_strip():
     """halo/device.py build_plan_table (the host table of b2s_halo_plan): 12 words per link, [10] = session rank that
-    owns the source strip, offsets relative to the field; the device-side handshake relies on adjacency being symmetric
+    owns the source strip, [11] = destination sub-domain, offsets relative to the field; the device-side handshake relies on adjacency being symmetric
     (whoever I wait for also waits for me), and every halo cell must be covered exactly once."""
     import torch
 
@@ -217,7 +217,7 @@ def test_plan_tables_name_the_owner_of_every_strip():
             t = device.build_plan_table(part, n_gpus, gpu, f, ranks)
             assert t.shape[1] == device.PLAN_WORDS and t.dtype == np.int64
             assert len(t) >= 4 * nsub  # at least one strip per edge of every sub-domain
-            assert set(int(r) for r in t[:, 10]) <= set(ranks) and np.all(t[:, 11] == 0)
+            assert set(int(r) for r in t[:, 10]) <= set(ranks) and set(int(b) for b in t[:, 11]) == set(range(nsub))
             neighbours[ranks[gpu]] = {int(r) for r in t[:, 10] if r != ranks[gpu]}
             # destination cells: every edge-halo cell of every local sub-domain exactly once, none in the interior
             hits = np.zeros(f.numel() + 64, dtype=np.int32)
