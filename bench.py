@@ -404,8 +404,10 @@ def main(argv=None) -> int:
             ms = float(t.item())
         region_ms.append(ms)
     t_wall1 = time.time()
+    halo_trace = None
     if ex is not None:
         ctx.check()  # no device-side wait timed out during the timed regions
+        halo_trace = ctx.trace()  # device timeline (ns) of the last timed step
     if ex is not None:
         launches_per_step = 1 if tr.fused else 2  # the fused step is one launch; else k_halo_exchange + fv_tp2d (gated or plain)
     else:
@@ -553,7 +555,7 @@ def main(argv=None) -> int:
                 "halo_bytes_over_nvlink_per_gpu_per_step": (ex.remote_bytes if ex is not None else tr.updater.bytes_sent_per_update),
                 "timed_regions": regions, "region_ms": [round(x, 4) for x in region_ms], "reported": "median region",
             },
-            "halo_check": halo_check, "device_step_equals_nccl_step": nccl_equal,
+            "halo_check": halo_check, "device_step_equals_nccl_step": nccl_equal, "halo_trace_ns": halo_trace,
             "roofline": roofline, "clocks": clocks, "hws": hws_summary, "gpu_launches": int(launches),
             "e2e": e2e, "cpu_baseline": cpu,
         }  # fmt: skip

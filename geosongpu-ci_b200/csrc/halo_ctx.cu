@@ -91,6 +91,7 @@ struct Plan {
   int nlinks = 0, nk = 0, max_strip = 0, elem_size = 0, nb = 0;
   void* field = nullptr;
   int64_t remote_bytes = 0;
+  unsigned long long peers = 0;  // ranks whose field some link reads
 };
 
 struct HaloCtx {
@@ -433,7 +434,7 @@ extern "C" int b2s_halo_plan(int64_t ctx, const void* field, int elem_size, int 
     D[10] = (int64_t) reinterpret_cast<intptr_t>(base);
     D[11] = (owner == c->rank ? 0 : owner + 1) | (dst_b << 16);
     if (L[8] * L[9] > p.max_strip) p.max_strip = (int)(L[8] * L[9]);
-    if (owner != c->rank) p.remote_bytes += L[8] * L[9] * nk * elem_size;
+    if (owner != c->rank) p.remote_bytes += L[8] * L[9] * nk * elem_size, p.peers |= 1ull << owner;
     per_b[dst_b] += 1;
     if (dst_b + 1 > p.nb) p.nb = (int)dst_b + 1;
   }
@@ -457,6 +458,7 @@ extern "C" int64_t b2s_halo_plan_remote_bytes(int64_t ctx, int plan) {
 static impl::HaloXchg xchg_of(const HaloCtx* c, const Plan& p, int gated) {
   impl::HaloXchg X;
   X.links = p.links_dev, X.peer_flags = c->peer_flags_dev, X.b_total = p.b_total_dev, X.state = c->state, X.dst = p.field;
+  X.peers = p.peers;
   X.nlinks = p.nlinks, X.nk = p.nk, X.my_rank = c->rank, X.world = c->world, X.gated = gated;
   return X;
 }

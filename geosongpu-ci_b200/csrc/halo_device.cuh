@@ -14,6 +14,7 @@ struct HaloXchg {
   const int* b_total;         // [64] work units (link, level) per destination sub-domain
   int* state;                 // [0] epoch, [1] blocks done, [2] status, [32 + b] units done, [128 + b] gate b, [200..] timeline
   void* dst;                  // this rank's field
+  unsigned long long peers;   // bit r set: some link reads rank r's field (the ranks whose announcement is awaited)
   int nlinks, nk, my_rank, world, gated;
 };
 
@@ -30,11 +31,14 @@ __device__ __forceinline__ void trace_ns(int* state, int slot) {
 }
 __device__ __forceinline__ void st_release_sys(int* p, int v) { asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ void st_release_gpu(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+__device__ __forceinline__ int ld_relaxed_sys(const int* p) {
   int v;
-  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// acquire / release fences (not the sequentially consistent __threadfence*: nothing here needs SC ordering)
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 
 __device__ __forceinline__ void strip_decode(int t, int nd, int np, int64_t ssd, int& d, int& p) {
   if (ssd == 1 || ssd == -1) {  // depth runs along i on the source side
@@ -57,15 +61,28 @@ __device__ __forceinline__ void halo_exchange_body(const HaloXchg& X, int* s_scr
   if (threadIdx.x == 0) *s_scratch = *reinterpret_cast<volatile int*>(state) + 1;
   __syncthreads();
   const int epoch = *s_scratch;
-  if (X.world > 1 && blockIdx.x == 0) {
+  if (X.world > 1) {
+    // block 0 announces "my field is final for this epoch" to every peer (one thread per peer) ...
+    if (blockIdx.x == 0)
+      for (int r = threadIdx.x; r < X.world; r += nthreads)
+        if (r != X.my_rank) st_release_sys(reinterpret_cast<int*>(static_cast<uintptr_t>(X.peer_flags[r])) + X.my_rank, epoch);
+    // ... and every block waits for the announcements of the ranks it may read, all at once: one thread per awaited
+    // peer polls its flag in this GPU's own memory (relaxed loads, no fence per poll), one acquire fence at the end
     for (int r = threadIdx.x; r < X.world; r += nthreads)
-      if (r != X.my_rank) {
-        __threadfence_system();
-        st_release_sys(reinterpret_cast<int*>(static_cast<uintptr_t>(X.peer_flags[r])) + X.my_rank, epoch);
+      if ((X.peers >> r) & 1ull) {
+        const int* mine = reinterpret_cast<const int*>(static_cast<uintptr_t>(X.peer_flags[X.my_rank])) + r;
+        const long long t0 = clock64();
+        while (ld_relaxed_sys(mine) < epoch) {
+          if (clock64() - t0 > kSyncTimeoutCycles) {
+            atomicExch(state + 2, 1);
+            break;
+          }
+        }
+        fence_acq_rel_sys();
       }
+    __syncthreads();
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) trace_ns(state, 0);
-  unsigned long long arrived = 0ull;  // peers whose announcement of this epoch has been seen (block-uniform)
   const int nk = X.nk, units = X.nlinks * nk;
   T* dst = static_cast<T*>(X.dst);
   int cur_b = -1, cur_n = 0;  // units of sub-domain cur_b this block has copied and not yet reported
@@ -75,7 +92,7 @@ __device__ __forceinline__ void halo_exchange_body(const HaloXchg& X, int* s_scr
     if (!X.gated || cur_n == 0) return;
     __syncthreads();
     if (threadIdx.x == 0) {
-      __threadfence();
+      fence_acq_rel_gpu();
       if (atomicAdd(state + kDoneWord + cur_b, cur_n) + cur_n == X.b_total[cur_b]) {
         state[kDoneWord + cur_b] = 0;
         st_release_gpu(state + kGateWord + cur_b, 1);
@@ -86,24 +103,10 @@ __device__ __forceinline__ void halo_exchange_body(const HaloXchg& X, int* s_scr
   for (int u = blockIdx.x; u < units; u += gridDim.x) {
     const int link = u / nk, k0 = u - link * nk;
     const int64_t* L = X.links + (int64_t)link * kExchangeWords;
-    const int src_rank = (int)(L[11] & 0xffff) - 1, dst_b = (int)(L[11] >> 16);
+    const int dst_b = (int)(L[11] >> 16);
     if (dst_b != cur_b) {
       report();
       cur_b = dst_b, cur_n = 0;
-    }
-    if (src_rank >= 0 && src_rank != X.my_rank && !((arrived >> src_rank) & 1ull)) {
-      if (threadIdx.x == 0) {
-        const int* mine = reinterpret_cast<const int*>(static_cast<uintptr_t>(X.peer_flags[X.my_rank])) + src_rank;
-        const long long t0 = clock64();
-        while (ld_acquire_sys(mine) < epoch) {
-          if (clock64() - t0 > kSyncTimeoutCycles) {
-            atomicExch(state + 2, 1);
-            break;
-          }
-        }
-      }
-      __syncthreads();
-      arrived |= 1ull << src_rank;
     }
     const int nd = (int)L[8], np = (int)L[9], n = nd * np;
     const T* src = reinterpret_cast<const T*>(static_cast<uintptr_t>(L[10])) + (L[0] + k0 * L[3]);
@@ -130,11 +133,11 @@ __device__ __forceinline__ void halo_exchange_body(const HaloXchg& X, int* s_scr
   // the last block of the launch advances the epoch for the next launch / graph replay
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
+    fence_acq_rel_gpu();
     if (atomicAdd(state + 1, 1) == (int)gridDim.x - 1) {
       state[1] = 0;
       trace_ns(state, 1);
-      __threadfence();
+      fence_acq_rel_gpu();
       *reinterpret_cast<volatile int*>(state) = epoch;
     }
   }

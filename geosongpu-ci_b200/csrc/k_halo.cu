@@ -129,8 +129,8 @@ int halo_pull(int nlinks, int nk, int max_strip, const int64_t* links, T* dst, c
 //     reads it at entry, the last block to finish advances it (state[1] counts blocks);
 //   * block 0 announces "my field is final for this epoch" to every peer: st.release.sys of the epoch into
 //     flags[my_rank] of each peer (the field was written by earlier kernels in stream order);
-//   * a block whose next strip reads a peer waits (ld.acquire.sys on its OWN flag array, a local poll) until that peer's
-//     announcement has arrived, then pulls.  Announcements are monotonic, a rank can run at most one step ahead of
+//   * every block first waits until the announcements of all the ranks it may read have arrived -- one thread per awaited
+//     peer polls this GPU's OWN flag array (relaxed loads, one acquire fence at the end) -- then pulls.  Announcements are monotonic, a rank can run at most one step ahead of
 //     a neighbour, and -- adjacency being symmetric -- a neighbour's announcement of epoch n+1 also says it has
 //     finished pulling epoch n from this rank, which is what a ping-pong time loop needs before overwriting;
 //   * gated: links are sorted by destination sub-domain b and carry it in word [11]; the last block of the links
@@ -160,7 +160,6 @@ __global__ void __launch_bounds__(256) k_halo_exchange(const HaloXchg X) {
 __global__ void k_halo_exchange_empty(int my_rank, int world, const int64_t* __restrict__ peer_flags, int* state, int nb, int gated) {
   const int epoch = *reinterpret_cast<volatile int*>(state) + 1;
   if ((int)threadIdx.x < world && (int)threadIdx.x != my_rank) {
-    __threadfence_system();
     st_release_sys(reinterpret_cast<int*>(static_cast<uintptr_t>(peer_flags[threadIdx.x])) + my_rank, epoch);
   }
   __syncthreads();
@@ -179,8 +178,10 @@ int halo_exchange_launch(int elem_size, int nb, const HaloXchg& X, cudaStream_t 
     return check_launch("halo_exchange");
   }
   B2S_ARGCHECK(X.nk > 0 && X.links && X.dst && X.b_total, "halo_exchange: bad sizes nlinks=%d nk=%d", X.nlinks, X.nk);
+  // beside a gated stencil (forked exchange): 2 blocks x 256 threads x ~50 registers per SM leave room for four stencil
+  // CTAs; alone on the GPU: every thread slot, the copy is bound by the number of (remote) loads in flight
   int per_sm = option("halo_blocks_per_sm", 0);
-  if (per_sm <= 0 || per_sm > 8) per_sm = 2;  // 2 x 256 threads x 54 registers leave room for four stencil CTAs per SM
+  if (per_sm <= 0 || per_sm > 8) per_sm = X.gated ? 2 : 8;
   const int64_t units = (int64_t)X.nlinks * X.nk;
   const int grid = (int)(units < (int64_t)sm_count() * per_sm ? units : (int64_t)sm_count() * per_sm);
   if (elem_size == 8)
