@@ -302,9 +302,17 @@ extern "C" int b2s_halo_init(const char* session, int rank, int world, int devic
   if (e == cudaSuccess) e = cudaMalloc(&c->state, kStateWords * sizeof(int));
   if (e == cudaSuccess) e = cudaMemset(c->state, 0, kStateWords * sizeof(int));
   if (e != cudaSuccess) return bail(fail_all(c, set_error((int)e, "b2s_halo_init: %s", cudaGetErrorString(e))));
+  // Load every kernel that can take part in a device-side wait NOW.  CUDA loads kernels lazily, at their first launch,
+  // and a load may have to wait for the context to go idle (and holds a driver lock meanwhile): a first launch issued
+  // while an exchange kernel spins on a neighbour -- whose own launch, in another thread of this process, needs that
+  // lock -- would stall until the spin times out.  After the final barrier below nothing of the path is left to load.
+  int rc = impl::halo_kernels_preload();
+  if (!rc) rc = impl::fv_tma_preload();
+  if (!rc) rc = impl::fv_stream_preload();
+  if (rc) return bail(fail_all(c, rc));
   // announcement flags: one int32 per rank, in peer-mapped memory, zero before anyone announces
   Allocation fl;
-  int rc = sym_alloc(c, (int64_t)sizeof(int) * kMaxRanks, &fl);
+  rc = sym_alloc(c, (int64_t)sizeof(int) * kMaxRanks, &fl);
   if (rc) return bail(rc);
   c->allocs.push_back(fl);
   c->flags = static_cast<int*>(fl.local);

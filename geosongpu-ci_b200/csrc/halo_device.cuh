@@ -55,7 +55,7 @@ __device__ __forceinline__ void strip_decode(int t, int nd, int np, int64_t ssd,
 // one after the other.  Protocol: see k_halo.cu.
 // s_scratch: one int of shared memory (the caller's, so that kernels with a dynamic TMA window keep it unpadded).
 template <typename T>
-__device__ __forceinline__ void halo_exchange_body(const HaloXchg& X, int* s_scratch) {
+__device__ __forceinline__ void halo_exchange_body_inl(const HaloXchg& X, int* s_scratch) {
   const int nthreads = blockDim.x;
   int* state = X.state;
   if (threadIdx.x == 0) *s_scratch = *reinterpret_cast<volatile int*>(state) + 1;
@@ -141,6 +141,14 @@ __device__ __forceinline__ void halo_exchange_body(const HaloXchg& X, int* s_scr
       *reinterpret_cast<volatile int*>(state) = epoch;
     }
   }
+}
+
+// The stencil kernels call the exchange as a REAL function: inlined, its register needs and code size changed the
+// allocation of the consumers' hot loop (tile kernel 91 -> 79 registers, +8 % run time at 3 x 192 x 192 x 72 even with
+// the exchange switched off, measured A/B against the round-1 library on one box).
+template <typename T>
+__device__ __noinline__ void halo_exchange_call(const HaloXchg* X, int* s_scratch) {
+  halo_exchange_body_inl<T>(*X, s_scratch);
 }
 
 }  // namespace impl

@@ -62,5 +62,13 @@ int halo_move(int nlinks, int nk, int max_strip, const int64_t* links, const T* 
 
 template <typename T>
 int halo_pull(int nlinks, int nk, int max_strip, const int64_t* links, T* dst, cudaStream_t s);
+
+// Per-device kernel set-up caches are indexed by the CUDA device ordinal.
+constexpr int kMaxDevices = 64;
+// Load (CUDA loads kernels lazily) and set up, on the current device, every kernel that can run beside -- or be
+// waited for by -- a spinning exchange kernel: called by b2s_halo_init, before the first exchange of the context.
+int fv_tma_preload();
+int fv_stream_preload();
+int halo_kernels_preload();
 }  // namespace impl
 }  // namespace b2s

@@ -15,6 +15,8 @@
 //     Nothing crosses threads except through the TMA-written rows: no __syncthreads in the loop.
 // Same formulas, same explicit-rounding arithmetic as the other variants: identical bits (tests assert it).
 // Algorithmic bytes/point: 40 R + 8 W + 8/nk; smem fill per point: (JB + 6) / JB of it.
+#include <mutex>
+
 #include "fv_math.cuh"
 #include "halo_device.cuh"
 #include "impl.cuh"
@@ -84,7 +86,8 @@ __device__ __forceinline__ StreamItem stream_item(int item, const FvStreamParams
   return it;
 }
 
-template <typename T, int TI, int NSTAGE>
+// GATED = false is the plain stencil without any of the gate / exchange code (see k_fv_tma.cu).
+template <typename T, int TI, int NSTAGE, bool GATED>
 __global__ void __launch_bounds__(TI + 32) k_fv_stream(const __grid_constant__ CUtensorMap tm_q,
                                                        const __grid_constant__ CUtensorMap tm_crx,
                                                        const __grid_constant__ CUtensorMap tm_xfx,
@@ -108,7 +111,9 @@ __global__ void __launch_bounds__(TI + 32) k_fv_stream(const __grid_constant__ C
     fence_barrier_init();
   }
   __syncthreads();
-  if (P.x.links != nullptr) halo_exchange_body<T>(P.x, reinterpret_cast<int*>(smem + G::SCRATCH_OFF));
+  if constexpr (GATED) {
+    if (P.x.links != nullptr) halo_exchange_call<T>(&P.x, reinterpret_cast<int*>(smem + G::SCRATCH_OFF));
+  }
 
   if (warp == NCONS_WARPS) {
     // =============================== PRODUCER ===============================
@@ -120,14 +125,16 @@ __global__ void __launch_bounds__(TI + 32) k_fv_stream(const __grid_constant__ C
       tma_prefetch_desc(&tm_yfx);
       int stage = 0;
       uint32_t phase = 0;
-      int b_open = P.gate == nullptr ? P.nb : 0;  // sub-domains below b_open have their halos (items run in b order)
+      [[maybe_unused]] int b_open = 0;  // sub-domains below b_open have their halos (items run in b order)
       for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
         const StreamItem it = stream_item(item, P);
         const int io = it.strip * TI;
-        while (b_open <= it.b) {
-          if (blockIdx.x == 0 && b_open == 0) gate_trace(P.gate, 3);
-          gate_acquire(P.gate, b_open++);
-          if (blockIdx.x == 0 && b_open == 1) gate_trace(P.gate, 4);
+        if constexpr (GATED) {
+          while (b_open <= it.b) {
+            if (blockIdx.x == 0 && b_open == 0) gate_trace(P.gate, 3);
+            gate_acquire(P.gate, b_open++);
+            if (blockIdx.x == 0 && b_open == 1) gate_trace(P.gate, 4);
+          }
         }
         for (int m = 0; m < it.nchunk; ++m) {
           // chunk row rr of chunk m is iteration n = m*RB + rr: q row r = jb0 - 3 + n (tensor row r + 3: the map is
@@ -225,7 +232,33 @@ __global__ void __launch_bounds__(TI + 32) k_fv_stream(const __grid_constant__ C
       for (int u = 0; u < RB; ++u) ra_cur[u] = ra_nxt[u];
     }
   }
-  if (P.gate != nullptr && threadIdx.x == 0) gate_release(P.gate, P.nb, gridDim.x);  // this CTA has consumed all its loads
+  if constexpr (GATED) {
+    if (threadIdx.x == 0) gate_release(P.gate, P.nb, gridDim.x);  // this CTA has consumed all its loads
+  }
+}
+
+// Shared-memory opt-in + resident-CTA count of one instance on the current device (cached per device); the first call
+// loads the kernel -- see kernel_setup in k_fv_tma.cu for why b2s_halo_init does that up front (fv_stream_preload).
+template <typename T, int TI, int NSTAGE>
+int stream_kernel_setup(bool gated, int* ctas_per_sm) {
+  using G = STile<T, TI, NSTAGE>;
+  static std::mutex mu;
+  static int cache[2][kMaxDevices] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+  std::lock_guard<std::mutex> lk(mu);
+  int& slot = cache[gated ? 1 : 0][dev];
+  if (slot == 0) {
+    auto kern = gated ? k_fv_stream<T, TI, NSTAGE, true> : k_fv_stream<T, TI, NSTAGE, false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
+    if (e != cudaSuccess) return set_error((int)e, "fv_tp2d(stream): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    int nblk = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, kern, G::THREADS, G::SMEM_BYTES);
+    if (e != cudaSuccess || nblk < 1) return set_error(e == cudaSuccess ? B2S_EUNSUPPORTED : (int)e, "fv_tp2d(stream): occupancy query failed");
+    slot = nblk;
+  }
+  *ctas_per_sm = slot;
+  return B2S_OK;
 }
 
 template <typename T, int TI, int NSTAGE>
@@ -248,16 +281,10 @@ int launch_stream(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j1
                   make_map<T>(&mcy, fcy.base, cry.sj, cry.sk, cry.sb, ni + fcy.off, nj + 1, nk, nb, G::BY, RB) &&
                   make_map<T>(&myx, fyx.base, yfx.sj, yfx.sk, yfx.sb, ni + fyx.off, nj + 1, nk, nb, G::BY, RB);
   if (!ok) return B2S_OK;
-  auto kern = k_fv_stream<T, TI, NSTAGE>;
-  static int ctas_per_sm = 0;
-  if (ctas_per_sm == 0) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
-    if (e != cudaSuccess) return set_error((int)e, "fv_tp2d(stream): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    int nblk = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, kern, G::THREADS, G::SMEM_BYTES);
-    if (e != cudaSuccess || nblk < 1) return set_error(e == cudaSuccess ? B2S_EUNSUPPORTED : (int)e, "fv_tp2d(stream): occupancy query failed");
-    ctas_per_sm = nblk;
-  }
+  const bool gated = gate != nullptr;
+  auto kern = gated ? k_fv_stream<T, TI, NSTAGE, true> : k_fv_stream<T, TI, NSTAGE, false>;
+  int ctas_per_sm = 0;
+  if (int rc = stream_kernel_setup<T, TI, NSTAGE>(gated, &ctas_per_sm)) return rc;
   FvStreamParams<T> P;
   P.nk = nk, P.i0 = i0, P.i1 = i1, P.j0 = j0, P.j1 = j1;
   P.nstrips = (i1 - i0 + TI - 1) / TI;
@@ -336,6 +363,28 @@ int fv_tp2d_stream(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j
   if (ti == 96) return launch_stream<T, 96, 3>(B2S_FVS_ARGS);
   if (ti == 64) return stages == 2 ? launch_stream<T, 64, 2>(B2S_FVS_ARGS) : (stages == 4 ? launch_stream<T, 64, 4>(B2S_FVS_ARGS) : launch_stream<T, 64, 3>(B2S_FVS_ARGS));
   return stages == 2 ? launch_stream<T, 128, 2>(B2S_FVS_ARGS) : (stages == 4 ? launch_stream<T, 128, 4>(B2S_FVS_ARGS) : launch_stream<T, 128, 3>(B2S_FVS_ARGS));
+}
+
+template <typename T>
+static int stream_preload_all() {
+  int n = 0, rc = 0;
+  for (int g = 0; g < 2; ++g) {
+    const bool gated = g != 0;
+    if ((rc = stream_kernel_setup<T, 32, 4>(gated, &n))) return rc;
+    if ((rc = stream_kernel_setup<T, 96, 3>(gated, &n))) return rc;
+    if ((rc = stream_kernel_setup<T, 64, 2>(gated, &n))) return rc;
+    if ((rc = stream_kernel_setup<T, 64, 3>(gated, &n))) return rc;
+    if ((rc = stream_kernel_setup<T, 64, 4>(gated, &n))) return rc;
+    if ((rc = stream_kernel_setup<T, 128, 2>(gated, &n))) return rc;
+    if ((rc = stream_kernel_setup<T, 128, 3>(gated, &n))) return rc;
+    if ((rc = stream_kernel_setup<T, 128, 4>(gated, &n))) return rc;
+  }
+  return B2S_OK;
+}
+// every instance fv_tp2d_stream can dispatch to, loaded and set up on the current device
+int fv_stream_preload() {
+  if (int rc = stream_preload_all<double>()) return rc;
+  return stream_preload_all<float>();
 }
 
 template int fv_tp2d_stream<double>(int, int, int, int, int, int, int, int, F3<const double>, F3<const double>,

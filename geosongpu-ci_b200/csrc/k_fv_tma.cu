@@ -18,6 +18,8 @@
 //   * every input element crosses HBM once; apron re-reads (q: (R+6)/R, cry/yfx: (R+1)/R) are
 //     L2 hits because neighbouring tiles are consecutive in the item order.
 // Algorithmic bytes/point: 40 R + 8 W + 8/nk (same as variant 1).
+#include <mutex>
+
 #include "fv_math.cuh"
 #include "halo_device.cuh"
 #include "impl.cuh"
@@ -117,7 +119,10 @@ struct ItemCursor {
   }
 };
 
-template <typename T, int TI, int R, int NSTAGE>
+// GATED = false is the plain stencil: it contains none of the gate / exchange code, so its register allocation and
+// schedule are exactly those of the kernel without the multi-GPU machinery (with the code merely switched off at run
+// time the consumers' loop came out 8 % slower at 3 x 192 x 192 x 72: ptxas re-allocated it, 91 -> 79 registers).
+template <typename T, int TI, int R, int NSTAGE, bool GATED>
 __global__ void __launch_bounds__(TI + 32) k_fv_tma(const __grid_constant__ CUtensorMap tm_q,
                                                     const __grid_constant__ CUtensorMap tm_crx,
                                                     const __grid_constant__ CUtensorMap tm_xfx,
@@ -145,7 +150,9 @@ __global__ void __launch_bounds__(TI + 32) k_fv_tma(const __grid_constant__ CUte
     fence_barrier_init();
   }
   __syncthreads();
-  if (P.x.links != nullptr) halo_exchange_body<T>(P.x, reinterpret_cast<int*>(smem + G::SCRATCH_OFF));
+  if constexpr (GATED) {
+    if (P.x.links != nullptr) halo_exchange_call<T>(&P.x, reinterpret_cast<int*>(smem + G::SCRATCH_OFF));
+  }
 
   ItemCursor cur;
   cur.init(blockIdx.x, gridDim.x, P.njblk, P.nstrips, P.nk);
@@ -161,14 +168,16 @@ __global__ void __launch_bounds__(TI + 32) k_fv_tma(const __grid_constant__ CUte
       tma_prefetch_desc(&tm_yfx);
       int stage = 0;
       uint32_t phase = 0;
-      int b_open = P.gate == nullptr ? P.nb : 0;  // sub-domains below b_open have their halos (items run in b order)
+      [[maybe_unused]] int b_open = 0;  // sub-domains below b_open have their halos (items run in b order)
       for (int n = 0; n < nmine; ++n) {
         const int io = cur.strip * TI;     // column offset of the tile inside the rectangle
         const int js = P.j0 + cur.jb * R;  // first compute row of the tile
-        while (b_open <= cur.b) {
-          if (blockIdx.x == 0 && b_open == 0) gate_trace(P.gate, 3);
-          gate_acquire(P.gate, b_open++);
-          if (blockIdx.x == 0 && b_open == 1) gate_trace(P.gate, 4);
+        if constexpr (GATED) {
+          while (b_open <= cur.b) {
+            if (blockIdx.x == 0 && b_open == 0) gate_trace(P.gate, 3);
+            gate_acquire(P.gate, b_open++);
+            if (blockIdx.x == 0 && b_open == 1) gate_trace(P.gate, 4);
+          }
         }
         mbar_wait(&empty[stage], phase ^ 1);
         unsigned char* st = smem + stage * G::STAGE_BYTES;
@@ -260,10 +269,38 @@ __global__ void __launch_bounds__(TI + 32) k_fv_tma(const __grid_constant__ CUte
       phase ^= 1;
     }
   }
-  if (P.gate != nullptr && threadIdx.x == 0) gate_release(P.gate, P.nb, gridDim.x);  // this CTA has consumed all its loads
+  if constexpr (GATED) {
+    if (threadIdx.x == 0) gate_release(P.gate, P.nb, gridDim.x);  // this CTA has consumed all its loads
+  }
 }
 
 // ---- host side (tensor maps: tma.cuh / tma_host.cu) ------------------------------------------------
+
+// Shared-memory opt-in and the resident-CTA count of one kernel instance on the CURRENT device, cached per device.
+// The first call also LOADS the kernel (CUDA loads modules lazily, and loading may have to wait for the context to go
+// idle): b2s_halo_init runs it for every instance (fv_tma_preload below) so that no load can happen later, while an
+// exchange kernel of this context is spinning on a neighbour that cannot launch until the load is over.
+template <typename T, int TI, int R, int NSTAGE>
+int kernel_setup(bool gated, int* ctas_per_sm) {
+  using G = Tile<T, TI, R, NSTAGE>;
+  static std::mutex mu;
+  static int cache[2][kMaxDevices] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+  std::lock_guard<std::mutex> lk(mu);
+  int& slot = cache[gated ? 1 : 0][dev];
+  if (slot == 0) {
+    auto kern = gated ? k_fv_tma<T, TI, R, NSTAGE, true> : k_fv_tma<T, TI, R, NSTAGE, false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
+    if (e != cudaSuccess) return set_error((int)e, "fv_tp2d(tma): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    int nblk = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, kern, G::THREADS, G::SMEM_BYTES);
+    if (e != cudaSuccess || nblk < 1) return set_error(e == cudaSuccess ? B2S_EUNSUPPORTED : (int)e, "fv_tp2d(tma): occupancy query failed");
+    slot = nblk;
+  }
+  *ctas_per_sm = slot;
+  return B2S_OK;
+}
 
 template <typename T, int TI, int R, int NSTAGE>
 int launch(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j1, F3<const T> q, F3<const T> crx,
@@ -287,16 +324,10 @@ int launch(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j1, F3<co
             make_map<T>(&myx, fyx.base, yfx.sj, yfx.sk, yfx.sb, ni + fyx.off, nj + 1, nk, nb, G::BY, G::RY);
   if (!ok) return B2S_OK;  // driver refused the descriptor: let the direct kernel handle the call
 
-  auto kern = k_fv_tma<T, TI, R, NSTAGE>;
-  static int ctas_per_sm = 0;
-  if (ctas_per_sm == 0) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
-    if (e != cudaSuccess) return set_error((int)e, "fv_tp2d(tma): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    int nblk = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, kern, G::THREADS, G::SMEM_BYTES);
-    if (e != cudaSuccess || nblk < 1) return set_error(e == cudaSuccess ? B2S_EUNSUPPORTED : (int)e, "fv_tp2d(tma): occupancy query failed");
-    ctas_per_sm = nblk;
-  }
+  const bool gated = gate != nullptr;
+  auto kern = gated ? k_fv_tma<T, TI, R, NSTAGE, true> : k_fv_tma<T, TI, R, NSTAGE, false>;
+  int ctas_per_sm = 0;
+  if (int rc = kernel_setup<T, TI, R, NSTAGE>(gated, &ctas_per_sm)) return rc;
   FvTmaParams<T> P;
   P.nk = nk;
   P.nb = nb;
@@ -390,6 +421,33 @@ int fv_tp2d_tma(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j1, 
     default:
       return launch_rows_stages<T, 128>(rows, stages, B2S_FV_ARGS);
   }
+}
+
+template <typename T, int TI>
+static int preload_rows_stages() {
+  int n = 0, rc = 0;
+  for (int g = 0; g < 2; ++g) {
+    if ((rc = kernel_setup<T, TI, 4, 2>(g != 0, &n))) return rc;
+    if ((rc = kernel_setup<T, TI, 4, 3>(g != 0, &n))) return rc;
+    if ((rc = kernel_setup<T, TI, 8, 2>(g != 0, &n))) return rc;
+    if ((rc = kernel_setup<T, TI, 8, 3>(g != 0, &n))) return rc;
+  }
+  return B2S_OK;
+}
+template <typename T>
+static int preload_all() {
+  int n = 0, rc = 0;
+  for (int g = 0; g < 2; ++g)
+    if ((rc = kernel_setup<T, 32, 8, 3>(g != 0, &n))) return rc;
+  if ((rc = preload_rows_stages<T, 64>())) return rc;
+  if ((rc = preload_rows_stages<T, 96>())) return rc;
+  if ((rc = preload_rows_stages<T, 128>())) return rc;
+  return preload_rows_stages<T, 192>();
+}
+// every instance fv_tp2d_tma can dispatch to, loaded and set up on the current device
+int fv_tma_preload() {
+  if (int rc = preload_all<double>()) return rc;
+  return preload_all<float>();
 }
 
 template int fv_tp2d_tma<double>(int, int, int, int, int, int, int, int, F3<const double>, F3<const double>,

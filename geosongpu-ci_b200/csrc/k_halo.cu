@@ -153,7 +153,7 @@ int halo_pull(int nlinks, int nk, int max_strip, const int64_t* links, T* dst, c
 template <typename T>
 __global__ void __launch_bounds__(256) k_halo_exchange(const HaloXchg X) {
   __shared__ int s_epoch;
-  halo_exchange_body<T>(X, &s_epoch);
+  halo_exchange_body_inl<T>(X, &s_epoch);
 }
 
 // an exchange without links still has to announce, advance the epoch and raise the gate
@@ -168,6 +168,16 @@ __global__ void k_halo_exchange_empty(int my_rank, int world, const int64_t* __r
     if (gated)
       for (int b = 0; b < nb; ++b) st_release_gpu(state + kGateWord + b, 1);
   }
+}
+
+// see impl.cuh: the kernels of the exchange itself, loaded before the first one can spin
+int halo_kernels_preload() {
+  cudaFuncAttributes a;
+  cudaError_t e = cudaFuncGetAttributes(&a, k_halo_exchange<double>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_halo_exchange<float>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_halo_exchange_empty);
+  if (e != cudaSuccess) return set_error((int)e, "halo exchange kernels: %s", cudaGetErrorString(e));
+  return B2S_OK;
 }
 
 int halo_exchange_launch(int elem_size, int nb, const HaloXchg& X, cudaStream_t s) {

@@ -8,6 +8,13 @@ import sys
 
 import pytest
 
+# The halo tests run several "virtual ranks" (threads) on ONE GPU, whose kernels wait for each other on the device.
+# With the default 8 hardware work queues two independent streams can share a queue, and a launch of one rank then sits
+# behind a pending wait of another -- a false dependency that the bounded device-side waits turn into a 2 s stall and a
+# status flag.  One queue per stream removes it.  (One rank per GPU -- the product configuration -- never shares queues
+# between ranks.)  Must be set before the CUDA context exists.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "geosongpu-ci_b200")):
     if p not in sys.path:
