@@ -28,17 +28,13 @@ DEFAULT_YAML = os.path.join(HERE, "b200stencil.yaml")
 REPO_ROOT = os.path.abspath(os.path.join(HERE, "..", "..", ".."))
 DEFAULT_HEADER = os.path.join(REPO_ROOT, "include", "b200stencil.h")
 DEFAULT_GLUE = os.path.abspath(os.path.join(HERE, "..", "..", "csrc", "abi_glue.inc"))
+DEFAULT_FORTRAN = os.path.join(REPO_ROOT, "include", "b2s_interface_mod.f90")
+DEFAULT_FORTRAN_EXAMPLE = os.path.join(REPO_ROOT, "include", "b2s_example.f90")
 
 PRECISIONS = {"double": ("double", "int64_t", ""), "float": ("float", "int32_t", "_f32")}
 
 _SCALARS = {"int": "int", "float": "float", "double": "double", "int64": "int64_t"}
 _ARRAYS = {"array_int": "int", "array_float": "float", "array_double": "double", "array_int64": "int64_t"}
-_F90_SCALARS = {
-    "int": "integer(kind=c_int), value",
-    "float": "real(kind=c_float), value",
-    "double": "real(kind=c_double), value",
-    "int64_t": "integer(kind=c_int64_t), value",
-}
 
 
 @dataclass
@@ -222,42 +218,17 @@ class Bridge:
         return "\n".join(out)
 
     def emit_fortran(self) -> str:
-        """``bind(c)`` interface module for Fortran callers (cf. templates/interface.f90.jinja2:1-56)."""
-        out = [
-            f"module {self.prefix}_interface_mod",
-            "   use iso_c_binding, only: c_int, c_int32_t, c_int64_t, c_float, c_double, c_ptr",
-            "   implicit none",
-            "   private",
-        ]
-        body = []
-        for fn in self.functions.values():
-            for precision in fn.precisions():
-                sym = fn.symbol(self.prefix, precision)
-                out.append(f"   public :: {sym}")
-                names, decls = [], []
-                for a in fn.arguments:
-                    t = a.element_ctype(precision)
-                    if a.is_array:
-                        # device pointers are opaque addresses on the Fortran side (type(c_ptr), value)
-                        names.append(a.name)
-                        decls.append(f"         type(c_ptr), value :: {a.name}")
-                        for s in a.stride_names():
-                            names.append(f"{a.name}_{s}")
-                            decls.append(f"         integer(kind=c_int64_t), value :: {a.name}_{s}")
-                    else:
-                        names.append(a.name)
-                        decls.append(f"         {_F90_SCALARS[t]} :: {a.name}")
-                names.append("stream")
-                decls.append("         type(c_ptr), value :: stream")
-                body += [
-                    f"      function {sym}({', '.join(names)}) bind(c, name='{sym}') result(status)",
-                    "         import c_int, c_int32_t, c_int64_t, c_float, c_double, c_ptr",
-                    *decls,
-                    "         integer(kind=c_int) :: status",
-                    f"      end function {sym}",
-                ]
-        out += ["   interface", *body, "   end interface", f"end module {self.prefix}_interface_mod", ""]
-        return "\n".join(out)
+        """``bind(c)`` interface module for Fortran callers (cf. templates/interface.f90.jinja2:1-56): the stencil entry
+        points plus the runtime / halo lifecycle, lines wrapped to 100 columns (``bridge/fortran.py``)."""
+        from . import fortran
+
+        return fortran.emit_module(self)
+
+    def emit_fortran_example(self) -> str:
+        """The Fortran acceptance program (cf. test/py_ftn_interface/data/fortran_program.f90)."""
+        from . import fortran
+
+        return fortran.emit_example_program(self)
 
 
 RUNTIME_SYMBOLS = [
@@ -409,22 +380,6 @@ B2S_API int b2s_halo_status(int64_t ctx, int* epoch, int* status);
 /* diagnostics, host-synchronising: device timeline (ns) of the last exchange + gated stencil: exchange start, exchange end,
  * gate 0 opened, first stencil CTA started, stencil CTA 0 passed gate 0, last stencil CTA finished */
 B2S_API int b2s_halo_trace(int64_t ctx, int64_t* out6);
-int b2s_halo_init(const char* session, int rank, int world, int device, int64_t* ctx);
-int b2s_halo_finalize(int64_t ctx);
-int b2s_halo_rank(int64_t ctx);
-int b2s_halo_world(int64_t ctx);
-int b2s_halo_barrier(int64_t ctx);
-int b2s_halo_alloc(int64_t ctx, int64_t nbytes, void** ptr);
-int b2s_halo_free(int64_t ctx, void* ptr);
-int b2s_halo_peer_ptr(int64_t ctx, const void* ptr, int peer, void** peer_ptr);
-int b2s_halo_plan(int64_t ctx, const void* field, int elem_size, int nk, int nlinks, const int64_t* links, int* plan);
-int64_t b2s_halo_plan_remote_bytes(int64_t ctx, int plan);
-int b2s_halo_exchange(int64_t ctx, int plan, void* stream);
-int b2s_halo_exchange_start(int64_t ctx, int plan, int gated, void* stream);
-int b2s_halo_exchange_wait(int64_t ctx, void* stream);
-int b2s_halo_gate(int64_t ctx, int** gate);
-int b2s_halo_status(int64_t ctx, int* epoch, int* status);
-int b2s_halo_trace(int64_t ctx, int64_t* out6);
 """
 
 HEADER_EPILOGUE = """#ifdef __cplusplus
@@ -439,7 +394,8 @@ def main(argv=None) -> int:
     ap.add_argument("definition", nargs="?", default=DEFAULT_YAML)
     ap.add_argument("--header", default=DEFAULT_HEADER)
     ap.add_argument("--glue", default=DEFAULT_GLUE)
-    ap.add_argument("--fortran", default=None)
+    ap.add_argument("--fortran", default=DEFAULT_FORTRAN)
+    ap.add_argument("--fortran-example", default=DEFAULT_FORTRAN_EXAMPLE)
     ap.add_argument("--check", action="store_true", help="fail if the header on disk is stale")
     ns = ap.parse_args(argv)
     bridge = Bridge.from_yaml(ns.definition)
@@ -455,6 +411,9 @@ def main(argv=None) -> int:
     if ns.fortran:
         with open(ns.fortran, "w") as f:
             f.write(bridge.emit_fortran())
+    if ns.fortran_example:
+        with open(ns.fortran_example, "w") as f:
+            f.write(bridge.emit_fortran_example())
     return 0
 
 

@@ -42,7 +42,7 @@
 
 namespace b2s {
 namespace impl {
-int halo_exchange_launch(int elem_size, int nb, const HaloXchg& X, cudaStream_t s);
+int halo_exchange_launch(int elem_size, int nb, const HaloXchg& X, bool narrow, cudaStream_t s);
 template <typename T>
 int fv_tp2d_fused(int ni, int nj, int nk, int nb, F3<const T> q, F3<const T> crx, F3<const T> xfx, F3<const T> cry,
                   F3<const T> yfx, F2<const T> rarea, F3<T> q_out, const HaloXchg& xchg, cudaStream_t s);
@@ -92,6 +92,7 @@ struct Plan {
   void* field = nullptr;
   int64_t remote_bytes = 0;
   unsigned long long peers = 0;  // ranks whose field some link reads
+  bool narrow = true;            // every strip offset relative to its (link, level chunk) origin fits 32 bits (k_halo_exchange2)
 };
 
 struct HaloCtx {
@@ -442,6 +443,11 @@ extern "C" int b2s_halo_plan(int64_t ctx, const void* field, int elem_size, int 
     D[10] = (int64_t) reinterpret_cast<intptr_t>(base);
     D[11] = (owner == c->rank ? 0 : owner + 1) | (dst_b << 16);
     if (L[8] * L[9] > p.max_strip) p.max_strip = (int)(L[8] * L[9]);
+    for (int side = 0; side < 2; ++side) {
+      const int64_t* S = L + 4 * side;  // [0] offset [1] depth stride [2] edge stride [3] level stride
+      const int64_t reach = L[8] * std::llabs(S[1]) + L[9] * std::llabs(S[2]) + impl::kMaxLevelsPerUnit * std::llabs(S[3]);
+      if (reach >= ((int64_t)1 << 31)) p.narrow = false;
+    }
     if (owner != c->rank) p.remote_bytes += L[8] * L[9] * nk * elem_size, p.peers |= 1ull << owner;
     per_b[dst_b] += 1;
     if (dst_b + 1 > p.nb) p.nb = (int)dst_b + 1;
@@ -474,7 +480,7 @@ static impl::HaloXchg xchg_of(const HaloCtx* c, const Plan& p, int gated) {
 static int launch_exchange(HaloCtx* c, int plan, int gated, cudaStream_t s) {
   if (plan < 0 || plan >= (int)c->plans.size()) return set_error(B2S_EINVAL, "b2s_halo_exchange: plan %d of %d", plan, (int)c->plans.size());
   const Plan& p = c->plans[plan];
-  return impl::halo_exchange_launch(p.elem_size, p.nb, xchg_of(c, p, gated), s);
+  return impl::halo_exchange_launch(p.elem_size, p.nb, xchg_of(c, p, gated), p.narrow, s);
 }
 
 // The transport step as ONE launch: halo update of the plan's field (neighbour handshake + strip copies over peer

@@ -143,6 +143,118 @@ __device__ __forceinline__ void halo_exchange_body_inl(const HaloXchg& X, int* s
   }
 }
 
+// ---- version 2 of the exchange body (the standalone kernel k_halo_exchange2, k_halo.cu) ----------------------------
+// Same protocol, same table, same gates; what changed is how the copy is fed:
+//   * a work unit is (link, chunk of `ku` levels) and a thread issues up to EIGHT independent loads before its first
+//     store -- at the 8-GPU sub-domain size the whole update (4 MB) is in flight after one batch, so its duration is
+//     one (NVLink) round trip instead of one per level;
+//   * the link table is staged in shared memory once per block (it was a dependent global load per unit);
+//   * the neighbours' announcements are awaited only before the first unit that reads a PEER: the same-GPU strips
+//     (sorted first inside each sub-domain) are copied while the announcements are still on their way.
+// s_links: kMaxCachedLinks * kExchangeWords int64 of shared memory; s_epoch: one int of shared memory.
+static constexpr int kMaxCachedLinks = 64;
+static constexpr int kLoadsInFlight = 8;
+static constexpr int kMaxLevelsPerUnit = 16;
+
+template <typename T>
+__device__ __forceinline__ void halo_exchange_body2(const HaloXchg& X, int ku, int* s_epoch, int64_t* s_links) {
+  const int nthreads = blockDim.x;
+  int* state = X.state;
+  if (threadIdx.x == 0) *s_epoch = *reinterpret_cast<volatile int*>(state) + 1;
+  const bool cached = X.nlinks <= kMaxCachedLinks;
+  if (cached)
+    for (int w = threadIdx.x; w < X.nlinks * kExchangeWords; w += nthreads) s_links[w] = X.links[w];
+  __syncthreads();
+  const int epoch = *s_epoch;
+  const int64_t* table = cached ? s_links : X.links;
+  // block 0 announces "my field is final for this epoch" to every peer (one thread per peer)
+  if (X.world > 1 && blockIdx.x == 0)
+    for (int r = threadIdx.x; r < X.world; r += nthreads)
+      if (r != X.my_rank) st_release_sys(reinterpret_cast<int*>(static_cast<uintptr_t>(X.peer_flags[r])) + X.my_rank, epoch);
+  bool awaited = X.world <= 1;
+  // every awaited peer at once: one thread per peer polls this GPU's own flag array, one acquire fence at the end
+  auto await_peers = [&]() {
+    for (int r = threadIdx.x; r < X.world; r += nthreads)
+      if ((X.peers >> r) & 1ull) {
+        const int* mine = reinterpret_cast<const int*>(static_cast<uintptr_t>(X.peer_flags[X.my_rank])) + r;
+        const long long t0 = clock64();
+        while (ld_relaxed_sys(mine) < epoch) {
+          if (clock64() - t0 > kSyncTimeoutCycles) {
+            atomicExch(state + 2, 1);
+            break;
+          }
+        }
+        fence_acq_rel_sys();
+      }
+    __syncthreads();
+    awaited = true;
+  };
+  if (blockIdx.x == 0 && threadIdx.x == 0) trace_ns(state, 0);
+  const int nk = X.nk, nchunks = (nk + ku - 1) / ku, units = X.nlinks * nchunks;
+  T* dst = static_cast<T*>(X.dst);
+  int cur_b = -1, cur_n = 0;  // (link, level) strips of sub-domain cur_b this block has copied and not yet reported
+  auto report = [&]() {
+    if (!X.gated || cur_n == 0) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      fence_acq_rel_gpu();
+      if (atomicAdd(state + kDoneWord + cur_b, cur_n) + cur_n == X.b_total[cur_b]) {
+        state[kDoneWord + cur_b] = 0;
+        st_release_gpu(state + kGateWord + cur_b, 1);
+        if (cur_b == 0) trace_ns(state, 2);
+      }
+    }
+  };
+  for (int u = blockIdx.x; u < units; u += gridDim.x) {
+    const int link = u / nchunks, k0 = (u - link * nchunks) * ku;
+    const int nlev = min(ku, nk - k0);
+    const int64_t* L = table + (int64_t)link * kExchangeWords;
+    const int dst_b = (int)(L[11] >> 16);
+    if (dst_b != cur_b) {
+      report();
+      cur_b = dst_b, cur_n = 0;
+    }
+    if (!awaited && (L[11] & 0xffff) != 0) await_peers();  // block-uniform: L is the same for every thread
+    const int nd = (int)L[8], np = (int)L[9], n = nd * np, total = n * nlev;
+    // 32-bit strides: b2s_halo_plan has checked that every offset relative to the unit's first element fits (kNarrow)
+    const int ssd = (int)L[1], ssp = (int)L[2], ssk = (int)L[3], dsd = (int)L[5], dsp = (int)L[6], dsk = (int)L[7];
+    const T* src = reinterpret_cast<const T*>(static_cast<uintptr_t>(L[10])) + (L[0] + k0 * L[3]);
+    T* out = dst + (L[4] + k0 * L[7]);
+    for (int e0 = threadIdx.x; e0 < total; e0 += kLoadsInFlight * nthreads) {
+      T v[kLoadsInFlight];
+      int o[kLoadsInFlight];
+#pragma unroll
+      for (int i = 0; i < kLoadsInFlight; ++i) {
+        const int e = e0 + i * nthreads;
+        if (e < total) {
+          const int kk = e / n, t = e - kk * n;
+          int d, p;
+          strip_decode(t, nd, np, ssd, d, p);
+          v[i] = src[d * ssd + p * ssp + kk * ssk];
+          o[i] = d * dsd + p * dsp + kk * dsk;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < kLoadsInFlight; ++i)
+        if (e0 + i * nthreads < total) out[o[i]] = v[i];
+    }
+    cur_n += nlev;
+  }
+  report();
+  if (!awaited) await_peers();  // a block without peer strips still may not let the kernel end before the neighbours announced
+  // the last block of the launch advances the epoch for the next launch / graph replay
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    fence_acq_rel_gpu();
+    if (atomicAdd(state + 1, 1) == (int)gridDim.x - 1) {
+      state[1] = 0;
+      trace_ns(state, 1);
+      fence_acq_rel_gpu();
+      *reinterpret_cast<volatile int*>(state) = epoch;
+    }
+  }
+}
+
 // The stencil kernels call the exchange as a REAL function: inlined, its register needs and code size changed the
 // allocation of the consumers' hot loop (tile kernel 91 -> 79 registers, +8 % run time at 3 x 192 x 192 x 72 even with
 // the exchange switched off, measured A/B against the round-1 library on one box).

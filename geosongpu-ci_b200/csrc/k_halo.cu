@@ -156,6 +156,16 @@ __global__ void __launch_bounds__(256) k_halo_exchange(const HaloXchg X) {
   halo_exchange_body_inl<T>(X, &s_epoch);
 }
 
+// version 2 (halo_device.cuh halo_exchange_body2): ku levels per work unit, eight loads in flight per thread, link table in
+// shared memory, announcements awaited only before the first peer strip.  b2s_set_option("halo_variant", 1) selects the
+// first version for A/B runs.
+template <typename T>
+__global__ void __launch_bounds__(256, 4) k_halo_exchange2(const HaloXchg X, int ku) {
+  __shared__ int s_epoch;
+  __shared__ int64_t s_links[kMaxCachedLinks * kExchangeWords];
+  halo_exchange_body2<T>(X, ku, &s_epoch, s_links);
+}
+
 // an exchange without links still has to announce, advance the epoch and raise the gate
 __global__ void k_halo_exchange_empty(int my_rank, int world, const int64_t* __restrict__ peer_flags, int* state, int nb, int gated) {
   const int epoch = *reinterpret_cast<volatile int*>(state) + 1;
@@ -175,12 +185,14 @@ int halo_kernels_preload() {
   cudaFuncAttributes a;
   cudaError_t e = cudaFuncGetAttributes(&a, k_halo_exchange<double>);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_halo_exchange<float>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_halo_exchange2<double>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_halo_exchange2<float>);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_halo_exchange_empty);
   if (e != cudaSuccess) return set_error((int)e, "halo exchange kernels: %s", cudaGetErrorString(e));
   return B2S_OK;
 }
 
-int halo_exchange_launch(int elem_size, int nb, const HaloXchg& X, cudaStream_t s) {
+int halo_exchange_launch(int elem_size, int nb, const HaloXchg& X, bool narrow, cudaStream_t s) {
   B2S_ARGCHECK(X.world >= 1 && X.world <= 64 && X.my_rank >= 0 && X.my_rank < X.world, "halo_exchange: rank %d of %d", X.my_rank, X.world);
   B2S_ARGCHECK(X.peer_flags && X.state, "halo_exchange: null pointer");
   if (X.nlinks == 0) {
@@ -188,16 +200,41 @@ int halo_exchange_launch(int elem_size, int nb, const HaloXchg& X, cudaStream_t 
     return check_launch("halo_exchange");
   }
   B2S_ARGCHECK(X.nk > 0 && X.links && X.dst && X.b_total, "halo_exchange: bad sizes nlinks=%d nk=%d", X.nlinks, X.nk);
-  // beside a gated stencil (forked exchange): 2 blocks x 256 threads x ~50 registers per SM leave room for four stencil
-  // CTAs; alone on the GPU: every thread slot, the copy is bound by the number of (remote) loads in flight
+  const int64_t units1 = (int64_t)X.nlinks * X.nk;  // (link, level) strips
   int per_sm = option("halo_blocks_per_sm", 0);
-  if (per_sm <= 0 || per_sm > 8) per_sm = X.gated ? 2 : 8;
-  const int64_t units = (int64_t)X.nlinks * X.nk;
-  const int grid = (int)(units < (int64_t)sm_count() * per_sm ? units : (int64_t)sm_count() * per_sm);
+  if (option("halo_variant", 0) == 1 || !narrow) {
+    // beside a gated stencil (forked exchange): 2 blocks x 256 threads x ~50 registers per SM leave room for four stencil
+    // CTAs; alone on the GPU: every thread slot, the copy is bound by the number of (remote) loads in flight
+    if (per_sm <= 0 || per_sm > 8) per_sm = X.gated ? 2 : 8;
+    const int grid = (int)(units1 < (int64_t)sm_count() * per_sm ? units1 : (int64_t)sm_count() * per_sm);
+    if (elem_size == 8)
+      k_halo_exchange<double><<<grid, 256, 0, s>>>(X);
+    else
+      k_halo_exchange<float><<<grid, 256, 0, s>>>(X);
+    return check_launch("halo_exchange");
+  }
+  // Version 2.  Gated (forked beside a stencil): a persistent grid of 2 blocks per SM -- thousands of blocks would take
+  // every thread slot and keep the stencil from becoming resident (profiles/r02_overlap.md) -- with as many levels per
+  // unit as it takes to hand every block about one unit.  Alone on the stream: one block per (link, level) strip, all
+  // of it in flight at once.
+  int grid, ku = option("halo_levels_per_unit", 0);
+  if (X.gated) {
+    if (per_sm <= 0 || per_sm > 4) per_sm = 2;
+    const int64_t slots = (int64_t)sm_count() * per_sm;
+    if (ku <= 0 || ku > kMaxLevelsPerUnit) ku = (int)((units1 + slots - 1) / slots);
+    ku = ku < 1 ? 1 : (ku > kMaxLevelsPerUnit ? kMaxLevelsPerUnit : ku);
+    const int64_t units = (int64_t)X.nlinks * ((X.nk + ku - 1) / ku);
+    grid = (int)(units < slots ? units : slots);
+  } else {
+    if (ku <= 0 || ku > kMaxLevelsPerUnit) ku = 1;
+    const int64_t units = (int64_t)X.nlinks * ((X.nk + ku - 1) / ku);
+    const int64_t cap = per_sm > 0 && per_sm <= 4 ? (int64_t)sm_count() * per_sm : ((int64_t)1 << 20);
+    grid = (int)(units < cap ? units : cap);
+  }
   if (elem_size == 8)
-    k_halo_exchange<double><<<grid, 256, 0, s>>>(X);
+    k_halo_exchange2<double><<<grid, 256, 0, s>>>(X, ku);
   else
-    k_halo_exchange<float><<<grid, 256, 0, s>>>(X);
+    k_halo_exchange2<float><<<grid, 256, 0, s>>>(X, ku);
   return check_launch("halo_exchange");
 }
 

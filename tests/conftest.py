@@ -41,3 +41,20 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """-m gpu runs: the pointwise relative errors every assert_close saw (tests/gpu_util.py), for profiles/."""
+    mod = sys.modules.get("gpu_util")
+    rows = getattr(mod, "POINTWISE", None) if mod else None
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    if not rows or not os.path.isdir(out_dir):
+        return
+    import json
+
+    try:
+        with open(os.path.join(out_dir, "parity_pointwise.jsonl"), "w") as f:
+            for r in rows:
+                f.write(json.dumps(r) + "\n")
+    except OSError:
+        pass

@@ -86,3 +86,46 @@ def test_halo_lifecycle_from_c(halo_driver):
     r = subprocess.run([exe], env=env, capture_output=True, text=True, timeout=180)
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
     assert "halo_driver ok" in r.stdout
+
+
+@pytest.fixture(scope="module")
+def fortran_mirror(tmp_path_factory):
+    """tests/c_abi/fortran_mirror.c: the call sequence of include/b2s_example.f90 in C (no Fortran compiler here)."""
+    if shutil.which("gcc") is None or not os.path.exists(os.path.join(CUDA, "include", "cuda_runtime_api.h")):
+        pytest.skip("gcc or the CUDA runtime headers are not available")
+    return _compile(tmp_path_factory, "fortran_mirror")
+
+
+def test_fortran_mirror_follows_the_fortran_program():
+    """The mirror makes the library calls of the generated Fortran program, in the same order."""
+    import re
+
+    from b200stencil.bridge import generate
+
+    f90 = generate.Bridge.from_yaml().emit_fortran_example()
+    c = open(os.path.join(ROOT, "tests", "c_abi", "fortran_mirror.c")).read()
+    body = f90[f90.index("implicit none"):]
+    calls_f = re.findall(r"\b(b2s_\w+)\s*\(", body)
+    calls_c = [m for m in re.findall(r"\b(b2s_\w+)\s*\(", c[c.index("int main"):]) if m != "b2s_last_error"]
+    assert calls_f == calls_c, (calls_f, calls_c)
+    for n in re.findall(r"stop (\d+)", f90):
+        if n == "1":
+            continue  # b2s_init failure: the C drivers all exit with 3 there (the no-GPU test keys on it)
+        assert f"STOP({n}," in c or f"return {n};" in c, f"stop {n} of the Fortran program has no counterpart"
+
+
+@pytest.mark.skipif(_has_cuda(), reason="this is the no-GPU behaviour")
+def test_fortran_mirror_fails_loudly_without_a_gpu(fortran_mirror):
+    exe, env = fortran_mirror
+    r = subprocess.run([exe], env=env, capture_output=True, text=True, timeout=60)
+    assert r.returncode == 3, (r.returncode, r.stdout, r.stderr)
+    assert "b2s_init" in r.stderr and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+def test_fortran_call_sequence_on_the_device(fortran_mirror):
+    """init, halo context, symmetric allocations, plan, exchange, status, fv_tp2d, finalize -- as the Fortran program does."""
+    exe, env = fortran_mirror
+    r = subprocess.run([exe], env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "b2s_example: ok" in r.stdout
