@@ -32,6 +32,11 @@ METRIC = "grid-cells x levels per second, fv_tp2d transport step (C384x72, 6 til
 UNIT = "points/s"
 
 
+def AUTO_STEP_MODE(n_gpus: int) -> str:
+    """How --step auto launches the device-exchange step (measured: profiles/README.md, round 2)."""
+    return "serial" if n_gpus == 1 else "overlap"
+
+
 def algorithmic_bytes_per_point(es: int) -> float:
     """40 R (q, crx, xfx, cry, yfx) + 8 W + 8/nk (rarea) in fp64; scales with the element size."""
     return 6 * es + es / NK
@@ -210,12 +215,13 @@ def main(argv=None) -> int:
     ap.add_argument("--step", choices=["auto", "fused", "overlap", "serial"], default="auto",
                     help="how the device-exchange step is launched: fused = ONE kernel (b2s_halo_fv_tp2d: the stencil grid shares the "
                          "exchange among its CTAs first, then computes behind per-sub-domain gates); overlap = exchange kernel forked "
-                         "beside one gated stencil launch; serial = exchange kernel, then stencil; auto = fused")
+                         "beside one gated stencil launch; serial = exchange kernel, then stencil; auto = serial on one GPU, overlap on several")
     ap.add_argument("--no-overlap", action="store_true", help="same as --step serial (and no interior/frame overlap on the NCCL baseline)")
     ap.add_argument("--halo", choices=["auto", "device", "nccl"], default="auto",
                     help="halo exchange: device (= auto) the library-owned exchange, ONE kernel per update (neighbour handshake "
                          "+ pull over NVLink peer memory, b2s_halo_*), forked next to a gated stencil launch; nccl = the "
                          "portable baseline: packed strips + grouped NCCL send/recv overlapped with an interior launch")
+    ap.add_argument("--option", action="append", default=[], help="libb200stencil tuning option name=value (b2s_set_option), repeatable")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly (default: the step is replayed from a CUDA graph at every N)")
     ap.add_argument("--regions", type=int, default=0, help="timed regions of K steps each (median reported); 0 = auto")
     ap.add_argument("--fused-remap", action="store_true", help="[chain] fold pe_prefix into the remap kernel (remap_delp)")
@@ -277,7 +283,12 @@ def main(argv=None) -> int:
     mk = lambda s, lo, hi: fields.empty(s, dtype, dev, batch=nsub).uniform_(lo, hi, generator=g)  # noqa: E731
     use_device = ns.halo in ("auto", "device")
     ctx = HaloContext(rank, world, local_rank)
-    step_mode = "serial" if ns.no_overlap else ("fused" if ns.step == "auto" else ns.step)
+    for opt in ns.option:
+        name, val = opt.split("=")
+        _abi.set_option(name, int(val))
+    # auto: one GPU hosts the whole cube, every link is a same-GPU copy and there is no latency to hide -> exchange, then
+    # stencil; several GPUs -> the exchange forked beside ONE gated stencil launch (see AUTO_STEP_MODE)
+    step_mode = "serial" if ns.no_overlap else (AUTO_STEP_MODE(n_gpus) if ns.step == "auto" else ns.step)
 
     # ---- halo_check: the exchange the timed loop uses, on a global-id field, every halo cell against geometry ----
     halo_check = None

@@ -67,9 +67,15 @@ class HostDeviceConversion:
         host = self._borrow(fptr, dim)
         if swap_axes:
             host = np.swapaxes(host, swap_axes[0], swap_axes[1])
-        with torch.cuda.stream(self._swap()):
-            dev = fields.empty(host.shape, torch.from_numpy(np.empty(0, host.dtype)).dtype, self._device)
+        # allocated on the CALLER's stream (that is where the field will be used and, later, freed: the caching
+        # allocator may then hand the block back to that stream only), uploaded on a working stream
+        consumer = torch.cuda.current_stream(self._device)
+        dev = fields.empty(host.shape, torch.from_numpy(np.empty(0, host.dtype)).dtype, self._device)
+        up = self._swap()
+        up.wait_stream(consumer)  # the block may still be in use by earlier work of the caller
+        with torch.cuda.stream(up):
             dev.copy_(torch.from_numpy(host), non_blocking=True)
+        dev.record_stream(up)
         return dev
 
     def device_to_fortran(self, field: torch.Tensor, fptr, swap_axes: Optional[Tuple[int, int]] = None) -> None:
@@ -82,9 +88,12 @@ class HostDeviceConversion:
             host = np.swapaxes(host, swap_axes[0], swap_axes[1])
         if torch.from_numpy(np.empty(0, host.dtype)).dtype != field.dtype:
             raise TypeError(f"device field is {field.dtype}, host buffer is {host.dtype}: the bridge does not cast")
-        with torch.cuda.stream(self._swap()) as _:
-            torch.cuda.current_stream().wait_stream(torch.cuda.default_stream(self._device))
+        producer = torch.cuda.current_stream(field.device)  # the stream the caller produced `field` on
+        down = self._swap()
+        down.wait_stream(producer)
+        with torch.cuda.stream(down):
             torch.from_numpy(host).copy_(field, non_blocking=False)
+        field.record_stream(down)
 
 
 # ---- pinned host fields ------------------------------------------------------------------------------

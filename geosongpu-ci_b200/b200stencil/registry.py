@@ -31,7 +31,31 @@ def _normalised(fn) -> str:
     if node.body and isinstance(node.body[0], ast.Expr) and isinstance(getattr(node.body[0], "value", None), ast.Constant) \
             and isinstance(node.body[0].value.value, str):
         node.body = node.body[1:]
-    return ast.dump(node, annotate_fields=False, include_attributes=False)
+    return _canonical(node)
+
+
+_SKIPPED_FIELDS = {"ctx", "type_comment", "kind", "type_params", "type_ignores"}
+
+
+def _canonical(node) -> str:
+    """A dump of the tree that does not depend on the interpreter version: ``ast.dump`` prints empty and ``None`` fields
+    up to Python 3.12 and omits them from 3.13 on, and 3.8 wraps subscripts in ``Index``.  Here a node is its class name
+    and its non-empty fields by name; load/store contexts and the fields newer grammars added are left out."""
+    if isinstance(node, ast.AST):
+        if type(node).__name__ == "Index":  # Python 3.8
+            return _canonical(node.value)
+        parts = []
+        for f in node._fields:
+            if f in _SKIPPED_FIELDS:
+                continue
+            v = getattr(node, f, None)
+            if v is None or v == []:
+                continue
+            parts.append(f"{f}={_canonical(v)}")
+        return f"{type(node).__name__}({','.join(parts)})"
+    if isinstance(node, list):
+        return "[" + ",".join(_canonical(x) for x in node) + "]"
+    return repr(node)
 
 
 def definition_key(fn) -> str:
@@ -113,8 +137,8 @@ def _install_builtin() -> None:
 
 
 # normalised-AST keys of the three dsl_patterns definitions
-KEY_TOP_OF_COLUMN = "2da85322528b5ef0"
-KEY_WHILE_IN_FUNCTION = "1f543e951c0c27fa"
-KEY_HYBRID_INDEX = "047faf4884cd586d"
+KEY_TOP_OF_COLUMN = "4171b7d0e0c22cb6"
+KEY_WHILE_IN_FUNCTION = "32099175f9960450"
+KEY_HYBRID_INDEX = "6e87534ceae78890"
 
 _install_builtin()

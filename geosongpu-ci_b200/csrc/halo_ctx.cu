@@ -42,7 +42,7 @@
 
 namespace b2s {
 namespace impl {
-int halo_exchange_launch(int elem_size, int nb, const HaloXchg& X, bool narrow, cudaStream_t s);
+int halo_exchange_launch(int elem_size, int nb, int max_strip, const HaloXchg& X, bool narrow, cudaStream_t s);
 template <typename T>
 int fv_tp2d_fused(int ni, int nj, int nk, int nb, F3<const T> q, F3<const T> crx, F3<const T> xfx, F3<const T> cry,
                   F3<const T> yfx, F2<const T> rarea, F3<T> q_out, const HaloXchg& xchg, cudaStream_t s);
@@ -480,7 +480,7 @@ static impl::HaloXchg xchg_of(const HaloCtx* c, const Plan& p, int gated) {
 static int launch_exchange(HaloCtx* c, int plan, int gated, cudaStream_t s) {
   if (plan < 0 || plan >= (int)c->plans.size()) return set_error(B2S_EINVAL, "b2s_halo_exchange: plan %d of %d", plan, (int)c->plans.size());
   const Plan& p = c->plans[plan];
-  return impl::halo_exchange_launch(p.elem_size, p.nb, xchg_of(c, p, gated), p.narrow, s);
+  return impl::halo_exchange_launch(p.elem_size, p.nb, p.max_strip, xchg_of(c, p, gated), p.narrow, s);
 }
 
 // The transport step as ONE launch: halo update of the plan's field (neighbour handshake + strip copies over peer

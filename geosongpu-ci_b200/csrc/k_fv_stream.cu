@@ -86,8 +86,8 @@ __device__ __forceinline__ StreamItem stream_item(int item, const FvStreamParams
   return it;
 }
 
-// GATED = false is the plain stencil without any of the gate / exchange code (see k_fv_tma.cu).
-template <typename T, int TI, int NSTAGE, bool GATED>
+// MODE: 0 plain stencil, 1 gated, 2 exchange fused in front of the gates (see k_fv_tma.cu).
+template <typename T, int TI, int NSTAGE, int MODE>
 __global__ void __launch_bounds__(TI + 32) k_fv_stream(const __grid_constant__ CUtensorMap tm_q,
                                                        const __grid_constant__ CUtensorMap tm_crx,
                                                        const __grid_constant__ CUtensorMap tm_xfx,
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(TI + 32) k_fv_stream(const __grid_constant__ C
     fence_barrier_init();
   }
   __syncthreads();
-  if constexpr (GATED) {
+  if constexpr (MODE == 2) {
     if (P.x.links != nullptr) halo_exchange_call<T>(&P.x, reinterpret_cast<int*>(smem + G::SCRATCH_OFF));
   }
 
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(TI + 32) k_fv_stream(const __grid_constant__ C
       for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
         const StreamItem it = stream_item(item, P);
         const int io = it.strip * TI;
-        if constexpr (GATED) {
+        if constexpr (MODE != 0) {
           while (b_open <= it.b) {
             if (blockIdx.x == 0 && b_open == 0) gate_trace(P.gate, 3);
             gate_acquire(P.gate, b_open++);
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(TI + 32) k_fv_stream(const __grid_constant__ C
       for (int u = 0; u < RB; ++u) ra_cur[u] = ra_nxt[u];
     }
   }
-  if constexpr (GATED) {
+  if constexpr (MODE != 0) {
     if (threadIdx.x == 0) gate_release(P.gate, P.nb, gridDim.x);  // this CTA has consumed all its loads
   }
 }
@@ -240,16 +240,16 @@ __global__ void __launch_bounds__(TI + 32) k_fv_stream(const __grid_constant__ C
 // Shared-memory opt-in + resident-CTA count of one instance on the current device (cached per device); the first call
 // loads the kernel -- see kernel_setup in k_fv_tma.cu for why b2s_halo_init does that up front (fv_stream_preload).
 template <typename T, int TI, int NSTAGE>
-int stream_kernel_setup(bool gated, int* ctas_per_sm) {
+int stream_kernel_setup(int mode, int* ctas_per_sm) {
   using G = STile<T, TI, NSTAGE>;
   static std::mutex mu;
-  static int cache[2][kMaxDevices] = {};
+  static int cache[3][kMaxDevices] = {};
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
   std::lock_guard<std::mutex> lk(mu);
-  int& slot = cache[gated ? 1 : 0][dev];
+  int& slot = cache[mode][dev];
   if (slot == 0) {
-    auto kern = gated ? k_fv_stream<T, TI, NSTAGE, true> : k_fv_stream<T, TI, NSTAGE, false>;
+    auto kern = mode == 2 ? k_fv_stream<T, TI, NSTAGE, 2> : (mode == 1 ? k_fv_stream<T, TI, NSTAGE, 1> : k_fv_stream<T, TI, NSTAGE, 0>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
     if (e != cudaSuccess) return set_error((int)e, "fv_tp2d(stream): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     int nblk = 0;
@@ -281,10 +281,10 @@ int launch_stream(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j1
                   make_map<T>(&mcy, fcy.base, cry.sj, cry.sk, cry.sb, ni + fcy.off, nj + 1, nk, nb, G::BY, RB) &&
                   make_map<T>(&myx, fyx.base, yfx.sj, yfx.sk, yfx.sb, ni + fyx.off, nj + 1, nk, nb, G::BY, RB);
   if (!ok) return B2S_OK;
-  const bool gated = gate != nullptr;
-  auto kern = gated ? k_fv_stream<T, TI, NSTAGE, true> : k_fv_stream<T, TI, NSTAGE, false>;
+  const int mode = xchg != nullptr ? 2 : (gate != nullptr ? 1 : 0);  // fused exchange + gates | gates only | plain
+  auto kern = mode == 2 ? k_fv_stream<T, TI, NSTAGE, 2> : (mode == 1 ? k_fv_stream<T, TI, NSTAGE, 1> : k_fv_stream<T, TI, NSTAGE, 0>);
   int ctas_per_sm = 0;
-  if (int rc = stream_kernel_setup<T, TI, NSTAGE>(gated, &ctas_per_sm)) return rc;
+  if (int rc = stream_kernel_setup<T, TI, NSTAGE>(mode, &ctas_per_sm)) return rc;
   FvStreamParams<T> P;
   P.nk = nk, P.i0 = i0, P.i1 = i1, P.j0 = j0, P.j1 = j1;
   P.nstrips = (i1 - i0 + TI - 1) / TI;
@@ -368,8 +368,7 @@ int fv_tp2d_stream(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j
 template <typename T>
 static int stream_preload_all() {
   int n = 0, rc = 0;
-  for (int g = 0; g < 2; ++g) {
-    const bool gated = g != 0;
+  for (int gated = 0; gated < 3; ++gated) {  // mode: plain, gated, fused
     if ((rc = stream_kernel_setup<T, 32, 4>(gated, &n))) return rc;
     if ((rc = stream_kernel_setup<T, 96, 3>(gated, &n))) return rc;
     if ((rc = stream_kernel_setup<T, 64, 2>(gated, &n))) return rc;

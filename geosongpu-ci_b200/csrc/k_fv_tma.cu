@@ -119,10 +119,11 @@ struct ItemCursor {
   }
 };
 
-// GATED = false is the plain stencil: it contains none of the gate / exchange code, so its register allocation and
+// MODE 0 is the plain stencil, 1 adds the gates (fv_tp2d_gated), 2 the exchange in front of them (halo_fv_tp2d: the call
+// into halo_exchange_call and its stack frame).  Mode 0 contains none of the gate / exchange code, so its register allocation and
 // schedule are exactly those of the kernel without the multi-GPU machinery (with the code merely switched off at run
 // time the consumers' loop came out 8 % slower at 3 x 192 x 192 x 72: ptxas re-allocated it, 91 -> 79 registers).
-template <typename T, int TI, int R, int NSTAGE, bool GATED>
+template <typename T, int TI, int R, int NSTAGE, int MODE>
 __global__ void __launch_bounds__(TI + 32) k_fv_tma(const __grid_constant__ CUtensorMap tm_q,
                                                     const __grid_constant__ CUtensorMap tm_crx,
                                                     const __grid_constant__ CUtensorMap tm_xfx,
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(TI + 32) k_fv_tma(const __grid_constant__ CUte
     fence_barrier_init();
   }
   __syncthreads();
-  if constexpr (GATED) {
+  if constexpr (MODE == 2) {
     if (P.x.links != nullptr) halo_exchange_call<T>(&P.x, reinterpret_cast<int*>(smem + G::SCRATCH_OFF));
   }
 
@@ -168,17 +169,10 @@ __global__ void __launch_bounds__(TI + 32) k_fv_tma(const __grid_constant__ CUte
       tma_prefetch_desc(&tm_yfx);
       int stage = 0;
       uint32_t phase = 0;
-      [[maybe_unused]] int b_open = 0;  // sub-domains below b_open have their halos (items run in b order)
-      for (int n = 0; n < nmine; ++n) {
+      // one item: wait for a free stage, five tile loads
+      auto issue = [&]() {
         const int io = cur.strip * TI;     // column offset of the tile inside the rectangle
         const int js = P.j0 + cur.jb * R;  // first compute row of the tile
-        if constexpr (GATED) {
-          while (b_open <= cur.b) {
-            if (blockIdx.x == 0 && b_open == 0) gate_trace(P.gate, 3);
-            gate_acquire(P.gate, b_open++);
-            if (blockIdx.x == 0 && b_open == 1) gate_trace(P.gate, 4);
-          }
-        }
         mbar_wait(&empty[stage], phase ^ 1);
         unsigned char* st = smem + stage * G::STAGE_BYTES;
         mbar_arrive_expect_tx(&full[stage], G::TX_BYTES);
@@ -192,6 +186,25 @@ __global__ void __launch_bounds__(TI + 32) k_fv_tma(const __grid_constant__ CUte
         if (++stage == NSTAGE) {
           stage = 0;
           phase ^= 1;
+        }
+      };
+      if constexpr (MODE == 0) {
+        for (int n = 0; n < nmine; ++n) issue();
+      } else {
+        // Items run in sub-domain order: the gate of sub-domain b is acquired ONCE, in front of this CTA's run of
+        // items of b, and the run itself is the plain loop (a gate test inside the item loop kept ptxas from
+        // unrolling it and made the gated kernel ~5 % slower than the plain one).
+        const int per_b = P.nitems / P.nb;
+        int n = 0;
+        for (int b = 0; b < P.nb && n < nmine; ++b) {
+          const int end_item = (b + 1) * per_b;  // my items below it: blockIdx.x + m * gridDim.x < end_item
+          int n_end = end_item > (int)blockIdx.x ? (end_item - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+          n_end = min(n_end, nmine);
+          if (n_end <= n) continue;
+          if (blockIdx.x == 0 && b == 0) gate_trace(P.gate, 3);
+          gate_acquire(P.gate, b);
+          if (blockIdx.x == 0 && b == 0) gate_trace(P.gate, 4);
+          for (; n < n_end; ++n) issue();
         }
       }
     }
@@ -269,7 +282,7 @@ __global__ void __launch_bounds__(TI + 32) k_fv_tma(const __grid_constant__ CUte
       phase ^= 1;
     }
   }
-  if constexpr (GATED) {
+  if constexpr (MODE != 0) {
     if (threadIdx.x == 0) gate_release(P.gate, P.nb, gridDim.x);  // this CTA has consumed all its loads
   }
 }
@@ -281,16 +294,16 @@ __global__ void __launch_bounds__(TI + 32) k_fv_tma(const __grid_constant__ CUte
 // idle): b2s_halo_init runs it for every instance (fv_tma_preload below) so that no load can happen later, while an
 // exchange kernel of this context is spinning on a neighbour that cannot launch until the load is over.
 template <typename T, int TI, int R, int NSTAGE>
-int kernel_setup(bool gated, int* ctas_per_sm) {
+int kernel_setup(int mode, int* ctas_per_sm) {
   using G = Tile<T, TI, R, NSTAGE>;
   static std::mutex mu;
-  static int cache[2][kMaxDevices] = {};
+  static int cache[3][kMaxDevices] = {};
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
   std::lock_guard<std::mutex> lk(mu);
-  int& slot = cache[gated ? 1 : 0][dev];
+  int& slot = cache[mode][dev];
   if (slot == 0) {
-    auto kern = gated ? k_fv_tma<T, TI, R, NSTAGE, true> : k_fv_tma<T, TI, R, NSTAGE, false>;
+    auto kern = mode == 2 ? k_fv_tma<T, TI, R, NSTAGE, 2> : (mode == 1 ? k_fv_tma<T, TI, R, NSTAGE, 1> : k_fv_tma<T, TI, R, NSTAGE, 0>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
     if (e != cudaSuccess) return set_error((int)e, "fv_tp2d(tma): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     int nblk = 0;
@@ -324,10 +337,10 @@ int launch(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j1, F3<co
             make_map<T>(&myx, fyx.base, yfx.sj, yfx.sk, yfx.sb, ni + fyx.off, nj + 1, nk, nb, G::BY, G::RY);
   if (!ok) return B2S_OK;  // driver refused the descriptor: let the direct kernel handle the call
 
-  const bool gated = gate != nullptr;
-  auto kern = gated ? k_fv_tma<T, TI, R, NSTAGE, true> : k_fv_tma<T, TI, R, NSTAGE, false>;
+  const int mode = xchg != nullptr ? 2 : (gate != nullptr ? 1 : 0);  // fused exchange + gates | gates only | plain
+  auto kern = mode == 2 ? k_fv_tma<T, TI, R, NSTAGE, 2> : (mode == 1 ? k_fv_tma<T, TI, R, NSTAGE, 1> : k_fv_tma<T, TI, R, NSTAGE, 0>);
   int ctas_per_sm = 0;
-  if (int rc = kernel_setup<T, TI, R, NSTAGE>(gated, &ctas_per_sm)) return rc;
+  if (int rc = kernel_setup<T, TI, R, NSTAGE>(mode, &ctas_per_sm)) return rc;
   FvTmaParams<T> P;
   P.nk = nk;
   P.nb = nb;
@@ -426,19 +439,19 @@ int fv_tp2d_tma(int ni, int nj, int nk, int nb, int i0, int i1, int j0, int j1, 
 template <typename T, int TI>
 static int preload_rows_stages() {
   int n = 0, rc = 0;
-  for (int g = 0; g < 2; ++g) {
-    if ((rc = kernel_setup<T, TI, 4, 2>(g != 0, &n))) return rc;
-    if ((rc = kernel_setup<T, TI, 4, 3>(g != 0, &n))) return rc;
-    if ((rc = kernel_setup<T, TI, 8, 2>(g != 0, &n))) return rc;
-    if ((rc = kernel_setup<T, TI, 8, 3>(g != 0, &n))) return rc;
+  for (int g = 0; g < 3; ++g) {
+    if ((rc = kernel_setup<T, TI, 4, 2>(g, &n))) return rc;
+    if ((rc = kernel_setup<T, TI, 4, 3>(g, &n))) return rc;
+    if ((rc = kernel_setup<T, TI, 8, 2>(g, &n))) return rc;
+    if ((rc = kernel_setup<T, TI, 8, 3>(g, &n))) return rc;
   }
   return B2S_OK;
 }
 template <typename T>
 static int preload_all() {
   int n = 0, rc = 0;
-  for (int g = 0; g < 2; ++g)
-    if ((rc = kernel_setup<T, 32, 8, 3>(g != 0, &n))) return rc;
+  for (int g = 0; g < 3; ++g)
+    if ((rc = kernel_setup<T, 32, 8, 3>(g, &n))) return rc;
   if ((rc = preload_rows_stages<T, 64>())) return rc;
   if ((rc = preload_rows_stages<T, 96>())) return rc;
   if ((rc = preload_rows_stages<T, 128>())) return rc;

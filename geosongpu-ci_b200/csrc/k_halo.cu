@@ -192,7 +192,7 @@ int halo_kernels_preload() {
   return B2S_OK;
 }
 
-int halo_exchange_launch(int elem_size, int nb, const HaloXchg& X, bool narrow, cudaStream_t s) {
+int halo_exchange_launch(int elem_size, int nb, int max_strip, const HaloXchg& X, bool narrow, cudaStream_t s) {
   B2S_ARGCHECK(X.world >= 1 && X.world <= 64 && X.my_rank >= 0 && X.my_rank < X.world, "halo_exchange: rank %d of %d", X.my_rank, X.world);
   B2S_ARGCHECK(X.peer_flags && X.state, "halo_exchange: null pointer");
   if (X.nlinks == 0) {
@@ -213,24 +213,19 @@ int halo_exchange_launch(int elem_size, int nb, const HaloXchg& X, bool narrow, 
       k_halo_exchange<float><<<grid, 256, 0, s>>>(X);
     return check_launch("halo_exchange");
   }
-  // Version 2.  Gated (forked beside a stencil): a persistent grid of 2 blocks per SM -- thousands of blocks would take
-  // every thread slot and keep the stencil from becoming resident (profiles/r02_overlap.md) -- with as many levels per
-  // unit as it takes to hand every block about one unit.  Alone on the stream: one block per (link, level) strip, all
-  // of it in flight at once.
-  int grid, ku = option("halo_levels_per_unit", 0);
-  if (X.gated) {
-    if (per_sm <= 0 || per_sm > 4) per_sm = 2;
-    const int64_t slots = (int64_t)sm_count() * per_sm;
-    if (ku <= 0 || ku > kMaxLevelsPerUnit) ku = (int)((units1 + slots - 1) / slots);
-    ku = ku < 1 ? 1 : (ku > kMaxLevelsPerUnit ? kMaxLevelsPerUnit : ku);
-    const int64_t units = (int64_t)X.nlinks * ((X.nk + ku - 1) / ku);
-    grid = (int)(units < slots ? units : slots);
-  } else {
-    if (ku <= 0 || ku > kMaxLevelsPerUnit) ku = 1;
-    const int64_t units = (int64_t)X.nlinks * ((X.nk + ku - 1) / ku);
-    const int64_t cap = per_sm > 0 && per_sm <= 4 ? (int64_t)sm_count() * per_sm : ((int64_t)1 << 20);
-    grid = (int)(units < cap ? units : cap);
-  }
+  // Version 2: a persistent grid walks the (link, chunk of ku levels) units in link order, so sub-domains complete -- and
+  // their gates open -- one after the other.  ku: as many levels as make a unit ONE batch of loads (256 threads x 8 in
+  // flight = 2048 elements: 3 levels of a 3 x 192 strip, 1 of a 3 x 384 strip).  Blocks per SM: 2 beside a gated stencil
+  // (thousands of blocks would take every thread slot and keep the stencil from becoming resident,
+  // profiles/r02_overlap.md), 4 (the register limit) alone on the stream.
+  int ku = option("halo_levels_per_unit", 0);
+  if (ku <= 0 || ku > kMaxLevelsPerUnit) ku = (kLoadsInFlight * 256) / (max_strip > 0 ? max_strip : 1);
+  ku = ku < 1 ? 1 : (ku > kMaxLevelsPerUnit ? kMaxLevelsPerUnit : ku);
+  if (ku > X.nk) ku = X.nk;
+  if (per_sm <= 0 || per_sm > 4) per_sm = X.gated ? 2 : 4;
+  const int64_t slots = (int64_t)sm_count() * per_sm;
+  const int64_t units = (int64_t)X.nlinks * ((X.nk + ku - 1) / ku);
+  const int grid = (int)(units < slots ? units : slots);
   if (elem_size == 8)
     k_halo_exchange2<double><<<grid, 256, 0, s>>>(X, ku);
   else
