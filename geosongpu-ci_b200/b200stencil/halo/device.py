@@ -119,14 +119,16 @@ class HaloContext:
         return self._gate
 
     def plan(self, field: torch.Tensor, part: CubedSpherePartitioner, n_gpus: Optional[int] = None, gpu: Optional[int] = None,
-             ranks: Optional[Sequence[int]] = None) -> "HaloExchange":
+             ranks: Optional[Sequence[int]] = None, push: bool = True) -> "HaloExchange":
         """Bind the links that fill this GPU's halos to ``field`` (a tensor returned by :meth:`field`).
 
-        ``ranks[g]`` = session rank that hosts GPU ``g`` of the decomposition (default: identity)."""
+        ``ranks[g]`` = session rank that hosts GPU ``g`` of the decomposition (default: identity).  ``push`` (every rank
+        alike): the table also carries this GPU's outgoing strips, so that the ungated exchange can push what crosses
+        NVLink instead of pulling it (:func:`build_plan_table`); gated and fused exchanges pull regardless."""
         n_gpus = self.world if n_gpus is None else n_gpus
         gpu = self.rank if gpu is None else gpu
         ranks = list(ranks) if ranks is not None else list(range(n_gpus))
-        table = build_plan_table(part, n_gpus, gpu, field, ranks)
+        table = build_plan_table(part, n_gpus, gpu, field, ranks, push=bool(push) and n_gpus > 1)
         out = self._ffi.new("int*")
         tbl = np.ascontiguousarray(table, dtype=np.int64)
         _abi.check("b2s_halo_plan", self._lib.b2s_halo_plan(
@@ -164,23 +166,37 @@ class HaloContext:
             _abi.check("b2s_halo_finalize", self._lib.b2s_halo_finalize(h))
 
 
-def build_plan_table(part: CubedSpherePartitioner, n_gpus: int, gpu: int, field: torch.Tensor, ranks: Sequence[int]) -> np.ndarray:
+LINK_OUT = 1 << 32     # b2s_halo_plan: the row is an outgoing strip, [10] = rank that owns the destination sub-domain
+LINK_PUSHED = 1 << 33  # b2s_halo_plan: an incoming strip its owner pushes
+
+
+def build_plan_table(part: CubedSpherePartitioner, n_gpus: int, gpu: int, field: torch.Tensor, ranks: Sequence[int],
+                     push: bool = False) -> np.ndarray:
     """int64 [nlinks, 12] host table of ``b2s_halo_plan``: element offsets relative to ``field``'s first element,
-    [10] = session rank owning the source sub-domain, [11] = destination sub-domain (batch index)."""
+    [10] = session rank owning the source sub-domain, [11] = destination sub-domain (batch index).
+
+    ``push``: every strip that crosses GPUs is marked at both ends -- LINK_PUSHED on the incoming row of the GPU that
+    owns the destination, and an extra LINK_OUT row ([10] = rank owning the destination) in the table of the GPU that
+    owns the source -- so that the ungated exchange pulls the same-GPU strips and lets the owners push the rest
+    (stores over NVLink are posted, loads are round trips: csrc/halo_device.cuh, version 3)."""
     from .updater import FieldGeometry
 
     geo = FieldGeometry(field, part.halo)
     rows = []
-    for l in part.all_links():  # every link whose destination is one of my sub-domains
-        if part.gpu_of(l.dst, n_gpus) != gpu:
+    for l in part.all_links():
+        g_src, g_dst = part.gpu_of(l.src, n_gpus), part.gpu_of(l.dst, n_gpus)
+        if g_dst != gpu and not (push and g_src == gpu):
             continue
-        owner = part.gpu_of(l.src, n_gpus)
         b_src, b_dst = part.local_index(l.src, n_gpus), part.local_index(l.dst, n_gpus)
-        rows.append([
+        geometry = [
             geo.cell(b_src, l.si0, l.sj0), geo.step(l.sdi, l.sdj), geo.step(l.spi, l.spj), geo.sk,
             geo.cell(b_dst, l.di0, l.dj0), geo.step(l.ddi, l.ddj), geo.step(l.dpi, l.dpj), geo.sk,
-            l.nd, l.np_, int(ranks[owner]), b_dst,
-        ])  # fmt: skip
+            l.nd, l.np_,
+        ]  # fmt: skip
+        if g_dst == gpu:  # a strip into one of my sub-domains
+            rows.append(geometry + [int(ranks[g_src]), b_dst | (LINK_PUSHED if push and g_src != gpu else 0)])
+        if push and g_src == gpu and g_dst != gpu:  # a strip of mine that a peer needs
+            rows.append(geometry + [int(ranks[g_dst]), b_dst | LINK_OUT])
     return np.asarray(rows, dtype=np.int64).reshape(-1, PLAN_WORDS)
 
 

@@ -43,6 +43,7 @@
 namespace b2s {
 namespace impl {
 int halo_exchange_launch(int elem_size, int nb, int max_strip, const HaloXchg& X, bool narrow, cudaStream_t s);
+int halo_exchange3_launch(int elem_size, int max_strip, const HaloXchg3& X, cudaStream_t s);
 template <typename T>
 int fv_tp2d_fused(int ni, int nj, int nk, int nb, F3<const T> q, F3<const T> crx, F3<const T> xfx, F3<const T> cry,
                   F3<const T> yfx, F2<const T> rarea, F3<T> q_out, const HaloXchg& xchg, cudaStream_t s);
@@ -55,7 +56,7 @@ namespace {
 
 constexpr int kMaxRanks = 64;
 constexpr uint32_t kMagic = 0xB2005A10u;
-constexpr int kStateWords = 256;  // device state: [0] epoch [1] blocks done [2] status; [32 + b] blocks done of sub-domain b
+constexpr int kStateWords = 512;  // device state: [0] epoch [1] blocks done [2] status; [32 + b] strips done of sub-domain b; [320 + r] strips pushed to rank r
 constexpr int kGateOffset = 128;  // gate words: [b] halos of sub-domain b ready, [64] consumer CTAs done, [65] consumer status
 constexpr int kGateSlots = 64;
 
@@ -92,7 +93,14 @@ struct Plan {
   void* field = nullptr;
   int64_t remote_bytes = 0;
   unsigned long long peers = 0;  // ranks whose field some link reads
-  bool narrow = true;            // every strip offset relative to its (link, level chunk) origin fits 32 bits (k_halo_exchange2)
+  bool narrow = true;            // every strip offset relative to its (link, level chunk) origin fits 32 bits (k_halo_exchange2 / 3)
+  // the mixed table (k_halo_exchange3), present when the caller's table carries outgoing links: same-GPU strips pulled,
+  // strips that cross NVLink pushed by the rank that owns the source
+  int64_t* rows_dev = nullptr;   // [nrows, 14]
+  int* push_total_dev = nullptr; // [world]
+  int nrows = 0;
+  unsigned long long wait_a = 0, wait_d = 0;
+  bool mixed = false;
 };
 
 struct HaloCtx {
@@ -313,11 +321,11 @@ extern "C" int b2s_halo_init(const char* session, int rank, int world, int devic
   if (rc) return bail(fail_all(c, rc));
   // announcement flags: one int32 per rank, in peer-mapped memory, zero before anyone announces
   Allocation fl;
-  rc = sym_alloc(c, (int64_t)sizeof(int) * kMaxRanks, &fl);
+  rc = sym_alloc(c, (int64_t)sizeof(int) * 2 * kMaxRanks, &fl);  // A (announced) flags, then D (delivered) flags
   if (rc) return bail(rc);
   c->allocs.push_back(fl);
   c->flags = static_cast<int*>(fl.local);
-  e = cudaMemset(c->flags, 0, sizeof(int) * kMaxRanks);
+  e = cudaMemset(c->flags, 0, sizeof(int) * 2 * kMaxRanks);
   std::vector<int64_t> pf(world);
   for (int r = 0; r < world; ++r) pf[r] = (int64_t) reinterpret_cast<intptr_t>(fl.peers[r]);
   if (e == cudaSuccess) e = cudaMalloc(&c->peer_flags_dev, sizeof(int64_t) * world);
@@ -343,6 +351,8 @@ extern "C" int b2s_halo_finalize(int64_t ctx) {
   for (auto& p : c->plans) {
     if (p.links_dev) cudaFree(p.links_dev);
     if (p.b_total_dev) cudaFree(p.b_total_dev);
+    if (p.rows_dev) cudaFree(p.rows_dev);
+    if (p.push_total_dev) cudaFree(p.push_total_dev);
   }
   for (auto& a : c->allocs) sym_free(c, a);
   if (c->peer_flags_dev) cudaFree(c->peer_flags_dev);
@@ -411,7 +421,12 @@ extern "C" int b2s_halo_peer_ptr(int64_t ctx, const void* ptr, int peer, void** 
 
 // links: HOST array [nlinks, 12] int64 -- words 0..9 as for b2s_halo_move (offsets in elements relative to `field`, the
 // same on every rank: the allocation is symmetric), [10] = rank that owns the source sub-domain, [11] = destination
-// sub-domain (batch index of the field, < 64; 0 when the field is not batched).
+// sub-domain (batch index of the field, < 64; 0 when the field is not batched) in its low 16 bits.
+// Optional, for the push path of the ungated exchange (all ranks must mark the two ends of a strip consistently):
+//   [11] bit 32 (B2S_HALO_LINK_OUT)     the row is an OUTGOING strip: its source is on this rank, [10] is the rank that owns
+//                                       the DESTINATION sub-domain (whose batch index is in the low 16 bits);
+//   [11] bit 33 (B2S_HALO_LINK_PUSHED)  an incoming strip its owner pushes (the owner's table has the matching OUT row).
+// Gated and fused exchanges always pull every incoming strip, marked or not.
 extern "C" int b2s_halo_plan(int64_t ctx, const void* field, int elem_size, int nk, int nlinks, const int64_t* links, int* plan_out) {
   B2S_CTX(c, ctx, "b2s_halo_plan");
   if (!plan_out || !field || (elem_size != 4 && elem_size != 8) || nk <= 0 || nk > 65535 || nlinks < 0 || nlinks > 65535 || (nlinks && !links))
@@ -421,33 +436,45 @@ extern "C" int b2s_halo_plan(int64_t ctx, const void* field, int elem_size, int 
     return set_error(B2S_EINVAL, "b2s_halo_plan: the field must live in a b2s_halo_alloc buffer (peers read it over NVLink)");
   const int64_t off = a ? static_cast<const char*>(field) - static_cast<const char*>(a->local) : 0;
   DeviceGuard guard(c->device);
+  constexpr int64_t kOut = (int64_t)1 << 32, kPushed = (int64_t)1 << 33;
+  auto base_on = [&](int64_t rank) -> int64_t {
+    const char* base = a ? static_cast<const char*>(a->peers[rank]) + off : static_cast<const char*>(field);
+    return (int64_t) reinterpret_cast<intptr_t>(base);
+  };
   Plan p;
-  p.nlinks = nlinks, p.nk = nk, p.elem_size = elem_size, p.field = const_cast<void*>(field);
-  // stable sort by destination sub-domain (the gates of a gated exchange open in that order), and inside a sub-domain
-  // the strips read from this GPU before those read from peers: the copies that need no announcement go first
-  std::vector<int> order(nlinks);
-  for (int n = 0; n < nlinks; ++n) order[n] = n;
-  auto key = [&](int x) { return links[(size_t)x * 12 + 11] * 2 + (links[(size_t)x * 12 + 10] != c->rank ? 1 : 0); };
-  std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return key(x) < key(y); });
-  std::vector<int64_t> tbl((size_t)nlinks * 12);
-  std::vector<int> per_b(kGateSlots, 0);
+  p.nk = nk, p.elem_size = elem_size, p.field = const_cast<void*>(field);
+  // incoming strips: stable sort by destination sub-domain (the gates of a gated exchange open in that order), and
+  // inside a sub-domain the strips read from this GPU before those read from peers (they need no announcement)
+  std::vector<int> in, out;
   for (int n = 0; n < nlinks; ++n) {
-    const int64_t* L = links + (size_t)order[n] * 12;
-    const int64_t owner = L[10], dst_b = L[11];
-    if (owner < 0 || owner >= c->world) return set_error(B2S_EINVAL, "b2s_halo_plan: link %d names owner rank %lld of %d", order[n], (long long)owner, c->world);
-    if (dst_b < 0 || dst_b >= kGateSlots) return set_error(B2S_EINVAL, "b2s_halo_plan: link %d names destination sub-domain %lld (0 .. %d)", order[n], (long long)dst_b, kGateSlots - 1);
-    if (L[8] <= 0 || L[9] <= 0) return set_error(B2S_EINVAL, "b2s_halo_plan: link %d has an empty strip", order[n]);
-    int64_t* D = tbl.data() + (size_t)n * 12;
-    memcpy(D, L, 10 * sizeof(int64_t));
-    const char* base = a ? static_cast<const char*>(a->peers[owner]) + off : static_cast<const char*>(field);
-    D[10] = (int64_t) reinterpret_cast<intptr_t>(base);
-    D[11] = (owner == c->rank ? 0 : owner + 1) | (dst_b << 16);
-    if (L[8] * L[9] > p.max_strip) p.max_strip = (int)(L[8] * L[9]);
+    const int64_t* L = links + (size_t)n * 12;
+    const int64_t peer = L[10], dst_b = L[11] & 0xffff;
+    if (peer < 0 || peer >= c->world) return set_error(B2S_EINVAL, "b2s_halo_plan: link %d names rank %lld of %d", n, (long long)peer, c->world);
+    if (dst_b >= kGateSlots) return set_error(B2S_EINVAL, "b2s_halo_plan: link %d names destination sub-domain %lld (0 .. %d)", n, (long long)dst_b, kGateSlots - 1);
+    if (L[8] <= 0 || L[9] <= 0) return set_error(B2S_EINVAL, "b2s_halo_plan: link %d has an empty strip", n);
+    if ((L[11] & kOut) && peer == c->rank) return set_error(B2S_EINVAL, "b2s_halo_plan: link %d is marked outgoing but stays on rank %d", n, c->rank);
+    if ((L[11] & kPushed) && peer == c->rank) return set_error(B2S_EINVAL, "b2s_halo_plan: link %d is marked pushed but its source is on this rank", n);
     for (int side = 0; side < 2; ++side) {
       const int64_t* S = L + 4 * side;  // [0] offset [1] depth stride [2] edge stride [3] level stride
       const int64_t reach = L[8] * std::llabs(S[1]) + L[9] * std::llabs(S[2]) + impl::kMaxLevelsPerUnit * std::llabs(S[3]);
       if (reach >= ((int64_t)1 << 31)) p.narrow = false;
     }
+    if (L[8] * L[9] > p.max_strip) p.max_strip = (int)(L[8] * L[9]);
+    ((L[11] & kOut) ? out : in).push_back(n);
+    if (L[11] & (kOut | kPushed)) p.mixed = true;
+  }
+  auto key = [&](int x) { return (links[(size_t)x * 12 + 11] & 0xffff) * 2 + (links[(size_t)x * 12 + 10] != c->rank ? 1 : 0); };
+  std::stable_sort(in.begin(), in.end(), [&](int x, int y) { return key(x) < key(y); });
+  p.nlinks = (int)in.size();
+  std::vector<int64_t> tbl(in.size() * 12);
+  std::vector<int> per_b(kGateSlots, 0);
+  for (size_t n = 0; n < in.size(); ++n) {
+    const int64_t* L = links + (size_t)in[n] * 12;
+    const int64_t owner = L[10], dst_b = L[11] & 0xffff;
+    int64_t* D = tbl.data() + n * 12;
+    memcpy(D, L, 10 * sizeof(int64_t));
+    D[10] = base_on(owner);
+    D[11] = (owner == c->rank ? 0 : owner + 1) | (dst_b << 16);
     if (owner != c->rank) p.remote_bytes += L[8] * L[9] * nk * elem_size, p.peers |= 1ull << owner;
     per_b[dst_b] += 1;
     if (dst_b + 1 > p.nb) p.nb = (int)dst_b + 1;
@@ -455,9 +482,48 @@ extern "C" int b2s_halo_plan(int64_t ctx, const void* field, int elem_size, int 
   for (int& v : per_b) v *= nk;  // work units (link, level) per destination sub-domain
   B2S_CUDA(cudaMalloc(&p.b_total_dev, kGateSlots * sizeof(int)), "b2s_halo_plan: cudaMalloc");
   B2S_CUDA(cudaMemcpy(p.b_total_dev, per_b.data(), kGateSlots * sizeof(int), cudaMemcpyHostToDevice), "b2s_halo_plan: cudaMemcpy");
-  if (nlinks) {
+  if (!tbl.empty()) {
     B2S_CUDA(cudaMalloc(&p.links_dev, tbl.size() * sizeof(int64_t)), "b2s_halo_plan: cudaMalloc");
     B2S_CUDA(cudaMemcpy(p.links_dev, tbl.data(), tbl.size() * sizeof(int64_t), cudaMemcpyHostToDevice), "b2s_halo_plan: cudaMemcpy");
+  }
+  if (p.mixed) {
+    // mixed table: incoming strips that are not pushed (pulled: same-GPU ones first, they need no announcement), then the
+    // outgoing strips (pushed), grouped by destination rank so that the delivery flags go out one rank after the other
+    std::vector<int64_t> rows;
+    std::vector<int> push_total(c->world, 0);
+    auto add_row = [&](const int64_t* L, int64_t src_base, int64_t dst_base, int64_t peer, bool push) {
+      const size_t at = rows.size();
+      rows.resize(at + impl::kMixedWords, 0);
+      memcpy(rows.data() + at, L, 10 * sizeof(int64_t));
+      rows[at + 10] = src_base;
+      rows[at + 11] = (peer == c->rank ? 0 : peer + 1) | ((L[11] & 0xffff) << 16) | ((int64_t)(push ? 1 : 0) << 40);
+      rows[at + 12] = dst_base;
+    };
+    for (int pass = 0; pass < 2; ++pass)
+      for (int n : in) {
+        const int64_t* L = links + (size_t)n * 12;
+        if (L[11] & kPushed) {
+          if (pass == 0) p.wait_d |= 1ull << L[10];
+          continue;
+        }
+        if ((L[10] != c->rank) != (pass == 1)) continue;
+        add_row(L, base_on(L[10]), base_on(c->rank), L[10], false);
+        if (L[10] != c->rank) p.wait_a |= 1ull << L[10];
+      }
+    std::stable_sort(out.begin(), out.end(), [&](int x, int y) { return links[(size_t)x * 12 + 10] < links[(size_t)y * 12 + 10]; });
+    for (int n : out) {
+      const int64_t* L = links + (size_t)n * 12;
+      add_row(L, base_on(c->rank), base_on(L[10]), L[10], true);
+      push_total[L[10]] += nk;
+      p.wait_a |= 1ull << L[10];
+    }
+    p.nrows = (int)(rows.size() / impl::kMixedWords);
+    B2S_CUDA(cudaMalloc(&p.push_total_dev, sizeof(int) * c->world), "b2s_halo_plan: cudaMalloc");
+    B2S_CUDA(cudaMemcpy(p.push_total_dev, push_total.data(), sizeof(int) * c->world, cudaMemcpyHostToDevice), "b2s_halo_plan: cudaMemcpy");
+    if (!rows.empty()) {
+      B2S_CUDA(cudaMalloc(&p.rows_dev, rows.size() * sizeof(int64_t)), "b2s_halo_plan: cudaMalloc");
+      B2S_CUDA(cudaMemcpy(p.rows_dev, rows.data(), rows.size() * sizeof(int64_t), cudaMemcpyHostToDevice), "b2s_halo_plan: cudaMemcpy");
+    }
   }
   c->plans.push_back(p);
   *plan_out = (int)c->plans.size() - 1;
@@ -480,6 +546,16 @@ static impl::HaloXchg xchg_of(const HaloCtx* c, const Plan& p, int gated) {
 static int launch_exchange(HaloCtx* c, int plan, int gated, cudaStream_t s) {
   if (plan < 0 || plan >= (int)c->plans.size()) return set_error(B2S_EINVAL, "b2s_halo_exchange: plan %d of %d", plan, (int)c->plans.size());
   const Plan& p = c->plans[plan];
+  if (!gated && p.mixed && option("halo_push", 1) != 0) {
+    // the choice must be the same on every rank (a receiver waits for the deliveries its table announces): it depends
+    // only on the caller's table and on an option the caller sets on all ranks alike
+    if (!p.narrow) return set_error(B2S_EUNSUPPORTED, "b2s_halo_exchange: strides beyond 32 bits; plan without outgoing links (pull only) for this field");
+    impl::HaloXchg3 X;
+    X.rows = p.rows_dev, X.peer_flags = c->peer_flags_dev, X.push_total = p.push_total_dev, X.state = c->state;
+    X.wait_a = p.wait_a, X.wait_d = p.wait_d;
+    X.nrows = p.nrows, X.nk = p.nk, X.my_rank = c->rank, X.world = c->world;
+    return impl::halo_exchange3_launch(p.elem_size, p.max_strip, X, s);
+  }
   return impl::halo_exchange_launch(p.elem_size, p.nb, p.max_strip, xchg_of(c, p, gated), p.narrow, s);
 }
 

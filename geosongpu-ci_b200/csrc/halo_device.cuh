@@ -255,6 +255,132 @@ __device__ __forceinline__ void halo_exchange_body2(const HaloXchg& X, int ku, i
   }
 }
 
+// ---- version 3: the MIXED exchange (k_halo_exchange3, k_halo.cu) -- same-GPU strips are pulled, strips that cross
+// NVLink are PUSHED by the rank that owns the source -----------------------------------------------------------------
+// Why: loads on a peer address are round trips, and the link keeps only so many of them in flight -- measured on two
+// B200s the in-place pull of 4 MB of strips took ~30 us (~130 GB/s) with four or with eight loads in flight per thread
+// (profiles/README.md, round 2).  Stores are posted: the owner reads its own strip (local) and writes it into the
+// neighbour's halo; nothing waits for a round trip except the two flag hops.
+// Protocol per epoch n (A and D are int32 flag arrays in peer-mapped memory, one slot per rank):
+//   1. block 0 writes A[me] = n at every peer: "my field is final for epoch n AND my halos may be overwritten"
+//      (the previous consumer of the halos ran earlier in stream order);
+//   2. a unit that touches a peer (a pull FROM it or a push INTO it) first waits for A[peer] >= n;
+//   3. push units of peer r are counted; the block that completes the count of r fences (sys) and writes D[me] = n at r:
+//      "everything I owe you for epoch n has landed";
+//   4. before it ends, every block waits for D[r] >= n from every rank r that pushes into this one.
+// When the kernel has ended, the halos are complete (the stencil that follows in stream order may read them), and every
+// neighbour has announced epoch n, i.e. has finished reading what it needed of epoch n-1 -- the same guarantee a
+// ping-pong time loop got from the pull protocol.
+// Row words: 0..9 as in the link table, [10] base address of the source buffer, [11] = (peer + 1, 0 for a same-GPU
+// strip) | destination sub-domain << 16 | push << 40, [12] base address of the destination buffer, [13] unused.
+struct HaloXchg3 {
+  const int64_t* rows;        // [nrows, 14]
+  const int64_t* peer_flags;  // [world] address of every rank's flag array as mapped here: A at [0, 64), D at [64, 128)
+  const int* push_total;      // [world] (link, level) strips this rank pushes to each peer
+  int* state;                 // [0] epoch, [1] blocks done, [2] status, [kPushWord + r] strips pushed to r so far
+  unsigned long long wait_a;  // ranks whose announcement is awaited: sources of pulls across GPUs and targets of pushes
+  unsigned long long wait_d;  // ranks that push into this one
+  int nrows, nk, my_rank, world;
+};
+static constexpr int kMixedWords = 14;
+static constexpr int kPushWord = 320;
+static constexpr int kDeliveredOffset = 64;  // D flags follow the A flags in the flag array
+
+template <typename T>
+__device__ __forceinline__ void halo_exchange_body3(const HaloXchg3& X, int ku, int* s_epoch, int64_t* s_rows) {
+  const int nthreads = blockDim.x;
+  int* state = X.state;
+  if (threadIdx.x == 0) *s_epoch = *reinterpret_cast<volatile int*>(state) + 1;
+  const bool cached = X.nrows <= kMaxCachedLinks;
+  if (cached)
+    for (int w = threadIdx.x; w < X.nrows * kMixedWords; w += nthreads) s_rows[w] = X.rows[w];
+  __syncthreads();
+  const int epoch = *s_epoch;
+  const int64_t* table = cached ? s_rows : X.rows;
+  if (X.world > 1 && blockIdx.x == 0)
+    for (int r = threadIdx.x; r < X.world; r += nthreads)
+      if (r != X.my_rank) st_release_sys(reinterpret_cast<int*>(static_cast<uintptr_t>(X.peer_flags[r])) + X.my_rank, epoch);
+  // one thread per awaited rank polls this GPU's own flag array (A: offset 0, D: offset 64), one acquire fence each
+  auto await = [&](unsigned long long mask, int offset) {
+    for (int r = threadIdx.x; r < X.world; r += nthreads)
+      if ((mask >> r) & 1ull) {
+        const int* mine = reinterpret_cast<const int*>(static_cast<uintptr_t>(X.peer_flags[X.my_rank])) + offset + r;
+        const long long t0 = clock64();
+        while (ld_relaxed_sys(mine) < epoch) {
+          if (clock64() - t0 > kSyncTimeoutCycles) {
+            atomicExch(state + 2, 1);
+            break;
+          }
+        }
+        fence_acq_rel_sys();
+      }
+    __syncthreads();
+  };
+  bool announced = X.world <= 1 || X.wait_a == 0ull;
+  if (blockIdx.x == 0 && threadIdx.x == 0) trace_ns(state, 0);
+  const int nk = X.nk, nchunks = (nk + ku - 1) / ku, units = X.nrows * nchunks;
+  for (int u = blockIdx.x; u < units; u += gridDim.x) {
+    const int row = u / nchunks, k0 = (u - row * nchunks) * ku;
+    const int nlev = min(ku, nk - k0);
+    const int64_t* L = table + (int64_t)row * kMixedWords;
+    const int peer = (int)(L[11] & 0xffff) - 1;
+    const bool push = ((L[11] >> 40) & 1) != 0;
+    if (!announced && peer >= 0) {  // block-uniform
+      await(X.wait_a, 0);
+      announced = true;
+    }
+    const int nd = (int)L[8], np = (int)L[9], n = nd * np, total = n * nlev;
+    const int ssd = (int)L[1], ssp = (int)L[2], ssk = (int)L[3], dsd = (int)L[5], dsp = (int)L[6], dsk = (int)L[7];
+    const T* src = reinterpret_cast<const T*>(static_cast<uintptr_t>(L[10])) + (L[0] + k0 * L[3]);
+    T* out = reinterpret_cast<T*>(static_cast<uintptr_t>(L[12])) + (L[4] + k0 * L[7]);
+    // consecutive threads follow whichever of (d, p) is contiguous on the REMOTE side: the source of a pull, the
+    // destination of a push
+    const int order_stride = push ? dsd : ssd;
+    for (int e0 = threadIdx.x; e0 < total; e0 += kLoadsInFlight * nthreads) {
+      T v[kLoadsInFlight];
+      int o[kLoadsInFlight];
+#pragma unroll
+      for (int i = 0; i < kLoadsInFlight; ++i) {
+        const int e = e0 + i * nthreads;
+        if (e < total) {
+          const int kk = e / n, t = e - kk * n;
+          int d, p;
+          strip_decode(t, nd, np, order_stride, d, p);
+          v[i] = src[d * ssd + p * ssp + kk * ssk];
+          o[i] = d * dsd + p * dsp + kk * dsk;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < kLoadsInFlight; ++i)
+        if (e0 + i * nthreads < total) out[o[i]] = v[i];
+    }
+    if (push) {
+      __syncthreads();  // every thread's stores of this unit are issued ...
+      if (threadIdx.x == 0) {
+        fence_acq_rel_sys();  // ... and ordered, system-wide, before the count that may release the delivery flag
+        if (atomicAdd(state + kPushWord + peer, nlev) + nlev == X.push_total[peer]) {
+          state[kPushWord + peer] = 0;
+          fence_acq_rel_sys();
+          st_release_sys(reinterpret_cast<int*>(static_cast<uintptr_t>(X.peer_flags[peer])) + kDeliveredOffset + X.my_rank, epoch);
+        }
+      }
+    }
+  }
+  if (!announced) await(X.wait_a, 0);
+  if (X.wait_d != 0ull) await(X.wait_d, kDeliveredOffset);
+  // the last block of the launch advances the epoch for the next launch / graph replay
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    fence_acq_rel_gpu();
+    if (atomicAdd(state + 1, 1) == (int)gridDim.x - 1) {
+      state[1] = 0;
+      trace_ns(state, 1);
+      fence_acq_rel_gpu();
+      *reinterpret_cast<volatile int*>(state) = epoch;
+    }
+  }
+}
+
 // The stencil kernels call the exchange as a REAL function: inlined, its register needs and code size changed the
 // allocation of the consumers' hot loop (tile kernel 91 -> 79 registers, +8 % run time at 3 x 192 x 192 x 72 even with
 // the exchange switched off, measured A/B against the round-1 library on one box).

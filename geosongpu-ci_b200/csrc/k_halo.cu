@@ -166,6 +166,33 @@ __global__ void __launch_bounds__(256, 4) k_halo_exchange2(const HaloXchg X, int
   halo_exchange_body2<T>(X, ku, &s_epoch, s_links);
 }
 
+// version 3 (halo_device.cuh halo_exchange_body3): same-GPU strips pulled, strips that cross NVLink pushed by their owner
+template <typename T>
+__global__ void __launch_bounds__(256, 4) k_halo_exchange3(const HaloXchg3 X, int ku) {
+  __shared__ int s_epoch;
+  __shared__ int64_t s_rows[kMaxCachedLinks * kMixedWords];
+  halo_exchange_body3<T>(X, ku, &s_epoch, s_rows);
+}
+
+int halo_exchange3_launch(int elem_size, int max_strip, const HaloXchg3& X, cudaStream_t s) {
+  B2S_ARGCHECK(X.world >= 1 && X.world <= 64 && X.my_rank >= 0 && X.my_rank < X.world, "halo_exchange: rank %d of %d", X.my_rank, X.world);
+  B2S_ARGCHECK(X.peer_flags && X.state && X.push_total && X.nk > 0 && X.nrows >= 0 && (X.nrows == 0 || X.rows), "halo_exchange: bad mixed plan");
+  int ku = option("halo_levels_per_unit", 0);
+  if (ku <= 0 || ku > kMaxLevelsPerUnit) ku = (kLoadsInFlight * 256) / (max_strip > 0 ? max_strip : 1);
+  ku = ku < 1 ? 1 : (ku > kMaxLevelsPerUnit ? kMaxLevelsPerUnit : ku);
+  if (ku > X.nk) ku = X.nk;
+  int per_sm = option("halo_blocks_per_sm", 0);
+  if (per_sm <= 0 || per_sm > 4) per_sm = 4;
+  const int64_t slots = (int64_t)sm_count() * per_sm;
+  const int64_t units = (int64_t)X.nrows * ((X.nk + ku - 1) / ku);
+  const int grid = (int)(units < 1 ? 1 : (units < slots ? units : slots));  // a rank without strips still announces and waits
+  if (elem_size == 8)
+    k_halo_exchange3<double><<<grid, 256, 0, s>>>(X, ku);
+  else
+    k_halo_exchange3<float><<<grid, 256, 0, s>>>(X, ku);
+  return check_launch("halo_exchange");
+}
+
 // an exchange without links still has to announce, advance the epoch and raise the gate
 __global__ void k_halo_exchange_empty(int my_rank, int world, const int64_t* __restrict__ peer_flags, int* state, int nb, int gated) {
   const int epoch = *reinterpret_cast<volatile int*>(state) + 1;
@@ -187,6 +214,8 @@ int halo_kernels_preload() {
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_halo_exchange<float>);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_halo_exchange2<double>);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_halo_exchange2<float>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_halo_exchange3<double>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_halo_exchange3<float>);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_halo_exchange_empty);
   if (e != cudaSuccess) return set_error((int)e, "halo exchange kernels: %s", cudaGetErrorString(e));
   return B2S_OK;
@@ -202,7 +231,11 @@ int halo_exchange_launch(int elem_size, int nb, int max_strip, const HaloXchg& X
   B2S_ARGCHECK(X.nk > 0 && X.links && X.dst && X.b_total, "halo_exchange: bad sizes nlinks=%d nk=%d", X.nlinks, X.nk);
   const int64_t units1 = (int64_t)X.nlinks * X.nk;  // (link, level) strips
   int per_sm = option("halo_blocks_per_sm", 0);
-  if (option("halo_variant", 0) == 1 || !narrow) {
+  // auto: version 2 alone on the stream; version 1 beside a gated stencil -- measured on two GPUs (C384x72, round 2) the
+  // forked version 2 made the overlapped step three times longer (0.9 ms against 0.31 ms) while the serial steps of the two
+  // versions tied; its 64 registers per thread do not fit twice per SM beside three 160-thread stencil CTAs
+  const int variant = option("halo_variant", 0);
+  if (variant == 1 || (variant == 0 && X.gated) || !narrow) {
     // beside a gated stencil (forked exchange): 2 blocks x 256 threads x ~50 registers per SM leave room for four stencil
     // CTAs; alone on the GPU: every thread slot, the copy is bound by the number of (remote) loads in flight
     if (per_sm <= 0 || per_sm > 8) per_sm = X.gated ? 2 : 8;

@@ -39,6 +39,7 @@ def assert_close(got, want, rtol, name=""):
     share of points within rtol pointwise): fields that span many decades (ql: 0 .. 1e-3) carry cancellation error
     near their zeros that no implementation can avoid, so the pointwise figure is reported, not asserted; for fields
     of uniform magnitude (q_out, x, q2) the two bounds coincide."""
+    got_dtype = str(np.asarray(got).dtype)
     want = np.asarray(want, dtype=np.float64)
     got = np.asarray(got, dtype=np.float64)
     scale = np.abs(want).max() if want.size else 0.0
@@ -51,7 +52,7 @@ def assert_close(got, want, rtol, name=""):
         rel[nz] = err[nz] / np.abs(want[nz])
         rel[~nz & (err > 0)] = np.inf
         POINTWISE.append({
-            "name": name, "dtype": str(np.asarray(got).dtype), "rtol": rtol, "points": int(want.size), "field_max": float(scale),
+            "name": name, "dtype": got_dtype, "rtol": rtol, "points": int(want.size), "field_max": float(scale),
             "field_min_abs_nonzero": float(np.abs(want[nz]).min()) if nz.any() else 0.0,
             "worst_abs_err": float(err.max()), "worst_err_over_field_max": float(err.max() / scale) if scale else 0.0,
             "worst_pointwise_rel": float(rel.max()), "share_within_rtol_pointwise": float((rel <= rtol).mean()),

@@ -82,9 +82,12 @@ def _run_ranks(world, body):
 @pytest.mark.parametrize("n_gpus", [1, 2, 4, 8])
 @pytest.mark.parametrize("corners", [False, True])
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
-def test_device_exchange_virtual_ranks(n_gpus, corners, dtype, monkeypatch):
+@pytest.mark.parametrize("push", [True, False])
+def test_device_exchange_virtual_ranks(n_gpus, corners, dtype, push, monkeypatch):
     """b2s_halo_init .. exchange .. finalize with one thread per rank: rendezvous, symmetric allocation, handshake,
-    pull, epoch counter; every halo cell against geometry after each of three exchanges."""
+    epoch counter; every halo cell against geometry after each of three exchanges.  ``push``: the plan carries the
+    outgoing strips, so the ungated exchanges (reps 0 and 2) pull the same-GPU strips and PUSH what crosses ranks
+    (announce / deliver flags, k_halo_exchange3); the forked exchange of rep 1 goes the same way.  Without: pull only."""
     monkeypatch.setenv("B2S_RDV_TIMEOUT", "60")
     N, nk = 24, 3
     part = CubedSpherePartitioner(N, layout_for(n_gpus), corners=corners)
@@ -95,7 +98,7 @@ def test_device_exchange_virtual_ranks(n_gpus, corners, dtype, monkeypatch):
         ctx = HaloContext(rank, n_gpus, 0, session)
         try:
             f = ctx.field((part.nx + 6, part.ny + 6, nk), nsub, dtype)
-            ex = ctx.plan(f, part)
+            ex = ctx.plan(f, part, push=push)
             for rep in range(3):
                 for b in range(nsub):
                     f[b].copy_(torch.from_numpy(global_id_field(part, rank * nsub + b, nk)))
@@ -204,12 +207,14 @@ def test_gated_step_equals_exchange_then_stencil(variant, N, nk, dtype):
         ctx.finalize()
 
 
-@pytest.mark.parametrize("fused", [False, True])
+@pytest.mark.parametrize("mode", ["overlap", "fused", "serial"])
 @pytest.mark.parametrize("n_gpus", [2, 8])
-def test_gated_step_virtual_ranks(n_gpus, fused):
-    """Handshake + pull + gate together: every virtual rank runs overlapped (forked exchange beside the gated stencil)
-    or fused (ONE kernel per step) transport steps; results equal the exchange-in-process reference (CUDA halo_move
-    tables) followed by the plain stencil.  The domains are small, so all the ranks' grids are co-resident on the GPU."""
+def test_gated_step_virtual_ranks(n_gpus, mode):
+    """Handshake + exchange + gate together: every virtual rank runs overlapped (forked pull beside the gated stencil),
+    fused (ONE kernel per step) or serial (mixed pull / push exchange, then the plain stencil) transport steps; results
+    equal the exchange-in-process reference (CUDA halo_move tables) followed by the plain stencil.  The domains are
+    small, so all the ranks' grids are co-resident on the GPU."""
+    fused = mode == "fused"
     from b200stencil.halo.updater import exchange_in_process
 
     N, nk, dtype = 48, 2, torch.float64
@@ -237,7 +242,7 @@ def test_gated_step_virtual_ranks(n_gpus, fused):
             q = ctx.field((ni + 6, nj + 6, nk), nsub, dtype)
             q[:, 3:-3, 3:-3] = data[rank]["core"]
             ex = ctx.plan(q, part)
-            tr = FvTransport(part, n_gpus, rank, exchange="device", halo_exchange=ex, overlap=True, fused=fused)
+            tr = FvTransport(part, n_gpus, rank, exchange="device", halo_exchange=ex, overlap=mode != "serial", fused=fused)
             d = data[rank]
             torch.cuda.current_stream().synchronize()
             ctx.barrier()

@@ -109,3 +109,110 @@ def test_without_the_wait_the_model_catches_the_race():
         except Violation:
             caught += 1
     assert caught > 150
+
+
+# ---- the push protocol of the mixed exchange (csrc/halo_device.cuh, version 3) ---------------------------------------
+#
+#   step n of rank r:   announce   A[p][r] = n for every neighbour p: "my field of version n-1 is final AND the halos
+#                                  of the buffer that holds it may be overwritten"
+#                       push       for every neighbour p: wait A[r][p] >= n, write my interior (version n-1) into p's
+#                                  halo of buffer (n-1) % 2, then D[p][r] = n: "delivered"
+#                       wait       D[r][p] >= n for every neighbour p
+#                       compute    read buffer (n-1) % 2 (interior + halos), write version n into the OTHER buffer
+#
+#   * a push must not land in a halo its owner is still reading (the previous user of that buffer is compute n-2);
+#   * compute n must find version n-1 in every halo of the buffer it reads;
+#   * no deadlock.  With either wait removed the model must FAIL.
+
+
+def run_push_schedule(nb, steps, rng, wait_a=True, wait_d=True, buffers=2):
+    world = len(nb)
+    A = [[0] * world for _ in range(world)]
+    D = [[0] * world for _ in range(world)]
+    version = [[0, -1] for _ in range(world)]                       # interior version per ping-pong buffer
+    halo = [[{p: None for p in nb[r]} for _ in range(2)] for r in range(world)]  # halo[r][buf][p]: version pushed by p
+    single = buffers == 1  # the stencil reads the SAME field every step and writes elsewhere (bench.py's step)
+    reading = [None] * world                                       # buffer a rank's stencil is reading right now
+    pc = [{"n": 1, "phase": "announce", "todo": None} for _ in range(world)]
+    done, guard = 0, 0
+    while done < world:
+        guard += 1
+        assert guard < 400000, "scheduler did not terminate"
+        runnable = []
+        for r in range(world):
+            st = pc[r]
+            if st["n"] > steps:
+                continue
+            if st["phase"] == "push" and wait_a:
+                if any(A[r][p] >= st["n"] for p in st["todo"]):
+                    runnable.append(r)
+            elif st["phase"] == "wait" and wait_d:
+                if all(D[r][p] >= st["n"] for p in nb[r]):
+                    runnable.append(r)
+            else:
+                runnable.append(r)
+        if not runnable:
+            raise Violation("deadlock: every unfinished rank is waiting")
+        r = rng.choice(runnable)
+        st = pc[r]
+        n = st["n"]
+        buf = 0 if single else (n - 1) % 2
+        if st["phase"] == "announce":
+            for p in nb[r]:
+                A[p][r] = n
+            st["phase"], st["todo"] = "push", sorted(nb[r])
+        elif st["phase"] == "push":
+            ready = [p for p in st["todo"] if A[r][p] >= n] if wait_a else list(st["todo"])
+            p = rng.choice(ready)
+            if not single and version[r][buf] != n - 1:
+                raise Violation(f"rank {r} step {n}: pushes version {version[r][buf]} instead of {n - 1}")
+            if reading[p] == buf:
+                raise Violation(f"rank {r} step {n}: writes into halo buffer {buf} of rank {p} while {p}'s stencil reads it")
+            halo[p][buf][r] = n - 1
+            D[p][r] = n
+            st["todo"].remove(p)
+            if not st["todo"]:
+                st["phase"] = "wait"
+        elif st["phase"] == "wait":
+            st["phase"] = "compute_begin"
+        elif st["phase"] == "compute_begin":
+            for p in nb[r]:
+                if halo[r][buf][p] != n - 1:
+                    raise Violation(f"rank {r} step {n}: halo from rank {p} holds version {halo[r][buf][p]}, not {n - 1}")
+            reading[r] = buf
+            if not single:
+                version[r][n % 2] = None
+            st["phase"] = "compute_end"
+        else:  # compute_end
+            if not single:
+                version[r][n % 2] = n
+            reading[r] = None
+            st["n"], st["phase"] = n + 1, "announce"
+            if st["n"] > steps:
+                done += 1
+    return True
+
+
+@pytest.mark.parametrize("buffers", [1, 2])
+@pytest.mark.parametrize("n_gpus", [2, 4, 8])
+def test_push_protocol_orders_deliveries_and_reads(n_gpus, buffers):
+    nb = gpu_neighbours(n_gpus)
+    rng = random.Random(20241018 + n_gpus)
+    for _ in range(300):
+        assert run_push_schedule(nb, steps=5, rng=rng, buffers=buffers)
+
+
+@pytest.mark.parametrize("drop", ["announcement", "delivery"])
+def test_push_protocol_model_catches_a_missing_wait(drop):
+    """Deliveries alone keep a rank within one step of its neighbours, which is enough for a two-buffer time loop (the
+    push lands in the buffer the neighbour is NOT reading); with ONE buffer read every step (bench.py) the announcement
+    is what keeps a push out of a halo that is still being read."""
+    nb = gpu_neighbours(4)
+    rng = random.Random(7)
+    caught = 0
+    for _ in range(200):
+        try:
+            run_push_schedule(nb, steps=5, rng=rng, wait_a=drop != "announcement", wait_d=drop != "delivery", buffers=1)
+        except Violation:
+            caught += 1
+    assert caught > 150, caught
