@@ -222,6 +222,10 @@ def main(argv=None) -> int:
                          "+ pull over NVLink peer memory, b2s_halo_*), forked next to a gated stencil launch; nccl = the "
                          "portable baseline: packed strips + grouped NCCL send/recv overlapped with an interior launch")
     ap.add_argument("--option", action="append", default=[], help="libb200stencil tuning option name=value (b2s_set_option), repeatable")
+    ap.add_argument("--push", choices=["staged", "inplace", "off"], default="staged",
+                    help="[serial step, N > 1] strips that cross NVLink: staged (default) = pushed PACKED by their owner into a staging "
+                         "area behind the destination's field and unpacked there; inplace = pushed straight into the halo cells; "
+                         "off = every strip pulled in place")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly (default: the step is replayed from a CUDA graph at every N)")
     ap.add_argument("--regions", type=int, default=0, help="timed regions of K steps each (median reported); 0 = auto")
     ap.add_argument("--fused-remap", action="store_true", help="[chain] fold pe_prefix into the remap kernel (remap_delp)")
@@ -289,12 +293,15 @@ def main(argv=None) -> int:
     # auto: one GPU hosts the whole cube, every link is a same-GPU copy and there is no latency to hide -> exchange, then
     # stencil; several GPUs -> the exchange forked beside ONE gated stencil launch (see AUTO_STEP_MODE)
     step_mode = "serial" if ns.no_overlap else (AUTO_STEP_MODE(n_gpus) if ns.step == "auto" else ns.step)
+    stage_part = part if ns.push == "staged" else None  # reserve the staging area behind the exchanged fields
+    if ns.push == "off":
+        _abi.set_option("halo_push", 0)
 
     # ---- halo_check: the exchange the timed loop uses, on a global-id field, every halo cell against geometry ----
     halo_check = None
     if use_device:
         nk_chk = 2
-        idf = ctx.field((ni + 6, nj + 6, nk_chk), nsub, torch.float64)
+        idf = ctx.field((ni + 6, nj + 6, nk_chk), nsub, torch.float64, part=stage_part)
         for b in range(nsub):
             idf[b].copy_(torch.from_numpy(global_id_field(part, rank * nsub + b, nk_chk)))
         barrier()
@@ -316,7 +323,7 @@ def main(argv=None) -> int:
         barrier()
 
     if use_device:
-        q = ctx.field((ni + 6, nj + 6, NK), nsub, dtype)
+        q = ctx.field((ni + 6, nj + 6, NK), nsub, dtype, part=stage_part)
         q.uniform_(0.5, 1.5, generator=g)
         ex = ctx.plan(q, part)
         tr = FvTransport(part, n_gpus, rank, exchange="device", halo_exchange=ex, overlap=step_mode != "serial", fused=step_mode == "fused")
@@ -558,7 +565,9 @@ def main(argv=None) -> int:
                 "step_launch": (step_mode if ex is not None else "nccl"),
                 "halo_exchange": (("device, fused: ONE kernel per step (b2s_halo_fv_tp2d) -- neighbour handshake + pull over NVLink peer memory "
                                    "shared among the CTAs of the stencil grid, then fv_tp2d behind per-sub-domain gates" if tr.fused else
-                                   "device: one k_halo_exchange launch (neighbour handshake + pull over NVLink peer memory, b2s_halo_*)"
+                                   "device: one exchange launch (b2s_halo_*: neighbour handshake; same-GPU strips pulled, strips that cross NVLink "
+                                   + {"staged": "pushed packed into the destination's staging area and unpacked there", "inplace": "pushed into the halo cells",
+                                      "off": "pulled in place"}[ns.push if not tr.overlap else "off"] + ")"
                                    + (", forked beside one gated fv_tp2d launch (sub-domain b computed while the halos of b+1.. arrive)" if tr.overlap else ", then fv_tp2d"))
                                   if ex is not None else
                                   "nccl baseline: pack kernel + grouped NCCL send/recv + unpack kernel" if n_gpus > 1 else
@@ -620,7 +629,7 @@ def run_chain(ns) -> int:
 
     ctx = HaloContext(rank, world, local_rank)
     exchange = "device"
-    q = ctx.field((ni + 6, nj + 6, nk), nsub, dtype)
+    q = ctx.field((ni + 6, nj + 6, nk), nsub, dtype, part=part)
     q.uniform_(0.5, 1.5, generator=g)
     ex = ctx.plan(q, part)
     crx, cry = mk((ni + 1, nj, nk), -0.9, 0.9), mk((ni, nj + 1, nk), -0.9, 0.9)

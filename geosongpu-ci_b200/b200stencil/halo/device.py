@@ -77,6 +77,7 @@ class HaloContext:
         _abi.check("b2s_halo_init", lib.b2s_halo_init((session or "").encode(), self.rank, self.world, self.device, out))
         self.handle = int(out[0])
         self._gate = None
+        self._staging = {}  # data_ptr of a field -> (offset, length) in elements of the staging area behind it
 
     # ---- memory ---------------------------------------------------------------------------------
     def alloc(self, nbytes: int) -> int:
@@ -97,16 +98,27 @@ class HaloContext:
         raw = torch.as_tensor(_RawDeviceMemory(ptr, nbytes, self), device=torch.device("cuda", self.device))
         return raw.view(dtype)
 
-    def field(self, shape_ijk: Sequence[int], batch: int, dtype=torch.float64, fill: Optional[float] = 0.0) -> torch.Tensor:
-        """A batch field [b, i, j, k] (i-fastest, rows padded to 16 bytes) in symmetric memory (collective)."""
+    def field(self, shape_ijk: Sequence[int], batch: int, dtype=torch.float64, fill: Optional[float] = 0.0,
+              part: Optional[CubedSpherePartitioner] = None, n_gpus: Optional[int] = None) -> torch.Tensor:
+        """A batch field [b, i, j, k] (i-fastest, rows padded to 16 bytes) in symmetric memory (collective).
+
+        ``part``: also reserve, behind the field in the SAME allocation, the staging area :meth:`plan` needs to let the
+        peers deliver their strips packed (:func:`build_plan_table`); without it the crossing strips are pushed in place."""
         ni, nj, nk = (int(s) for s in shape_ijk)
         nip = _padded(ni, dtype)
         numel = int(batch) * nk * nj * nip
         es = torch.empty((), dtype=dtype).element_size()
-        flat = self._tensor(self.alloc(numel * es), numel * es, dtype)
+        align = 128 // es
+        staging_at = (numel + align - 1) // align * align
+        staging = staging_elements(part, self.world if n_gpus is None else n_gpus, nk) if part is not None else 0
+        total = staging_at + staging if staging else numel
+        flat = self._tensor(self.alloc(total * es), total * es, dtype)
         if fill is not None:
             flat.fill_(fill)
-        return flat.view(int(batch), nk, nj, nip).permute(0, 3, 2, 1)[:, :ni]
+        out = flat[:numel].view(int(batch), nk, nj, nip).permute(0, 3, 2, 1)[:, :ni]
+        if staging:
+            self._staging[out.data_ptr()] = (staging_at, staging)
+        return out
 
     # ---- exchange -------------------------------------------------------------------------------
     @property
@@ -128,7 +140,11 @@ class HaloContext:
         n_gpus = self.world if n_gpus is None else n_gpus
         gpu = self.rank if gpu is None else gpu
         ranks = list(ranks) if ranks is not None else list(range(n_gpus))
-        table = build_plan_table(part, n_gpus, gpu, field, ranks, push=bool(push) and n_gpus > 1)
+        at = self._staging.get(field.data_ptr())
+        if at is not None and at[1] < staging_elements(part, n_gpus, int(field.shape[3])):
+            raise ValueError("the staging area reserved behind this field is too small for this partitioner")
+        table = build_plan_table(part, n_gpus, gpu, field, ranks, push=bool(push) and n_gpus > 1,
+                                 staging_offset=at[0] if at is not None else None)
         out = self._ffi.new("int*")
         tbl = np.ascontiguousarray(table, dtype=np.int64)
         _abi.check("b2s_halo_plan", self._lib.b2s_halo_plan(
@@ -168,35 +184,72 @@ class HaloContext:
 
 LINK_OUT = 1 << 32     # b2s_halo_plan: the row is an outgoing strip, [10] = rank that owns the destination sub-domain
 LINK_PUSHED = 1 << 33  # b2s_halo_plan: an incoming strip its owner pushes
+LINK_STAGED = 1 << 34  # b2s_halo_plan: same-rank unpack of a strip rank [10] delivered into this rank's staging area
+
+
+def _crossing_links(part: CubedSpherePartitioner, n_gpus: int, gpu: int):
+    """Links whose destination is on ``gpu`` and whose source is on another GPU, in the partitioner's global order --
+    every rank enumerates them alike, which is what lets the two ends of a strip agree on its place in the staging area."""
+    return [l for l in part.all_links() if part.gpu_of(l.dst, n_gpus) == gpu and part.gpu_of(l.src, n_gpus) != gpu]
+
+
+def staging_elements(part: CubedSpherePartitioner, n_gpus: int, nk: int) -> int:
+    """Elements of staging area a GPU needs for the packed strips its peers deliver (the largest over the GPUs: the
+    allocation is symmetric)."""
+    if n_gpus <= 1:
+        return 0
+    return max(sum(l.nd * l.np_ for l in _crossing_links(part, n_gpus, g)) for g in range(n_gpus)) * int(nk)
 
 
 def build_plan_table(part: CubedSpherePartitioner, n_gpus: int, gpu: int, field: torch.Tensor, ranks: Sequence[int],
-                     push: bool = False) -> np.ndarray:
+                     push: bool = False, staging_offset: Optional[int] = None) -> np.ndarray:
     """int64 [nlinks, 12] host table of ``b2s_halo_plan``: element offsets relative to ``field``'s first element,
     [10] = session rank owning the source sub-domain, [11] = destination sub-domain (batch index).
 
     ``push``: every strip that crosses GPUs is marked at both ends -- LINK_PUSHED on the incoming row of the GPU that
     owns the destination, and an extra LINK_OUT row ([10] = rank owning the destination) in the table of the GPU that
     owns the source -- so that the ungated exchange pulls the same-GPU strips and lets the owners push the rest
-    (stores over NVLink are posted, loads are round trips: csrc/halo_device.cuh, version 3)."""
+    (stores over NVLink are posted, loads are round trips: csrc/halo_device.cuh, version 3).
+
+    ``staging_offset`` (with ``push``; elements from ``field``'s first element to a staging area inside the same
+    symmetric allocation, :func:`staging_elements` long): the owner pushes every crossing strip PACKED -- level by level,
+    in the order its own memory is contiguous in -- into the destination rank's staging area, so that everything that
+    travels over NVLink is contiguous (a west/east strip in place is 3 elements out of every 3 KB row), and the
+    destination rank unpacks it locally (LINK_STAGED rows) once the delivery flag has arrived."""
     from .updater import FieldGeometry
 
     geo = FieldGeometry(field, part.halo)
+    staged = bool(push) and staging_offset is not None
+
+    def segment(g_dst: int, link) -> int:  # first element of the link's packed strip in the staging area of g_dst
+        at = 0
+        for l in _crossing_links(part, n_gpus, g_dst):
+            if l.key == link.key:
+                return int(staging_offset) + at * geo.nk
+            at += l.nd * l.np_
+        raise KeyError(link.key)
+
     rows = []
     for l in part.all_links():
         g_src, g_dst = part.gpu_of(l.src, n_gpus), part.gpu_of(l.dst, n_gpus)
         if g_dst != gpu and not (push and g_src == gpu):
             continue
         b_src, b_dst = part.local_index(l.src, n_gpus), part.local_index(l.dst, n_gpus)
-        geometry = [
-            geo.cell(b_src, l.si0, l.sj0), geo.step(l.sdi, l.sdj), geo.step(l.spi, l.spj), geo.sk,
-            geo.cell(b_dst, l.di0, l.dj0), geo.step(l.ddi, l.ddj), geo.step(l.dpi, l.dpj), geo.sk,
-            l.nd, l.np_,
-        ]  # fmt: skip
+        src = [geo.cell(b_src, l.si0, l.sj0), geo.step(l.sdi, l.sdj), geo.step(l.spi, l.spj), geo.sk]
+        dst = [geo.cell(b_dst, l.di0, l.dj0), geo.step(l.ddi, l.ddj), geo.step(l.dpi, l.dpj), geo.sk]
+        size = [l.nd, l.np_]
+        crossing = g_src != g_dst
         if g_dst == gpu:  # a strip into one of my sub-domains
-            rows.append(geometry + [int(ranks[g_src]), b_dst | (LINK_PUSHED if push and g_src != gpu else 0)])
-        if push and g_src == gpu and g_dst != gpu:  # a strip of mine that a peer needs
-            rows.append(geometry + [int(ranks[g_dst]), b_dst | LINK_OUT])
+            rows.append(src + dst + size + [int(ranks[g_src]), b_dst | (LINK_PUSHED if push and crossing else 0)])
+        if not (push and crossing):
+            continue
+        # packed layout of the strip: one level after the other, depth fastest where the source's depth runs along i
+        n = l.nd * l.np_
+        packed = [segment(g_dst, l)] + ([1, l.nd] if abs(src[1]) == 1 else [l.np_, 1]) + [n] if staged else None
+        if g_src == gpu:  # a strip of mine that a peer needs
+            rows.append(src + (packed if staged else dst) + size + [int(ranks[g_dst]), b_dst | LINK_OUT])
+        if g_dst == gpu and staged:  # ... and its unpacking at the destination, once delivered
+            rows.append(packed + dst + size + [int(ranks[g_src]), b_dst | LINK_STAGED])
     return np.asarray(rows, dtype=np.int64).reshape(-1, PLAN_WORDS)
 
 

@@ -98,7 +98,7 @@ struct Plan {
   // strips that cross NVLink pushed by the rank that owns the source
   int64_t* rows_dev = nullptr;   // [nrows, 14]
   int* push_total_dev = nullptr; // [world]
-  int nrows = 0;
+  int nrows = 0, nrows1 = 0;     // rows [0, nrows1) before the deliveries are awaited, the rest after
   unsigned long long wait_a = 0, wait_d = 0;
   bool mixed = false;
 };
@@ -425,8 +425,12 @@ extern "C" int b2s_halo_peer_ptr(int64_t ctx, const void* ptr, int peer, void** 
 // Optional, for the push path of the ungated exchange (all ranks must mark the two ends of a strip consistently):
 //   [11] bit 32 (B2S_HALO_LINK_OUT)     the row is an OUTGOING strip: its source is on this rank, [10] is the rank that owns
 //                                       the DESTINATION sub-domain (whose batch index is in the low 16 bits);
-//   [11] bit 33 (B2S_HALO_LINK_PUSHED)  an incoming strip its owner pushes (the owner's table has the matching OUT row).
-// Gated and fused exchanges always pull every incoming strip, marked or not.
+//   [11] bit 33 (B2S_HALO_LINK_PUSHED)  an incoming strip its owner pushes (the owner's table has the matching OUT row);
+//   [11] bit 34 (B2S_HALO_LINK_STAGED)  a same-rank copy that must run AFTER the deliveries of rank [10] have arrived: the
+//                                       owner pushed the strip, packed, into a staging area of this rank's allocation (the
+//                                       OUT row's destination) and this row unpacks it into the halo.  Only the ungated
+//                                       exchange uses it; it comes in addition to the PUSHED row of the same strip.
+// Gated and fused exchanges always pull every incoming strip in place, marked or not.
 extern "C" int b2s_halo_plan(int64_t ctx, const void* field, int elem_size, int nk, int nlinks, const int64_t* links, int* plan_out) {
   B2S_CTX(c, ctx, "b2s_halo_plan");
   if (!plan_out || !field || (elem_size != 4 && elem_size != 8) || nk <= 0 || nk > 65535 || nlinks < 0 || nlinks > 65535 || (nlinks && !links))
@@ -436,7 +440,7 @@ extern "C" int b2s_halo_plan(int64_t ctx, const void* field, int elem_size, int 
     return set_error(B2S_EINVAL, "b2s_halo_plan: the field must live in a b2s_halo_alloc buffer (peers read it over NVLink)");
   const int64_t off = a ? static_cast<const char*>(field) - static_cast<const char*>(a->local) : 0;
   DeviceGuard guard(c->device);
-  constexpr int64_t kOut = (int64_t)1 << 32, kPushed = (int64_t)1 << 33;
+  constexpr int64_t kOut = (int64_t)1 << 32, kPushed = (int64_t)1 << 33, kStaged = (int64_t)1 << 34;
   auto base_on = [&](int64_t rank) -> int64_t {
     const char* base = a ? static_cast<const char*>(a->peers[rank]) + off : static_cast<const char*>(field);
     return (int64_t) reinterpret_cast<intptr_t>(base);
@@ -445,7 +449,7 @@ extern "C" int b2s_halo_plan(int64_t ctx, const void* field, int elem_size, int 
   p.nk = nk, p.elem_size = elem_size, p.field = const_cast<void*>(field);
   // incoming strips: stable sort by destination sub-domain (the gates of a gated exchange open in that order), and
   // inside a sub-domain the strips read from this GPU before those read from peers (they need no announcement)
-  std::vector<int> in, out;
+  std::vector<int> in, out, staged;
   for (int n = 0; n < nlinks; ++n) {
     const int64_t* L = links + (size_t)n * 12;
     const int64_t peer = L[10], dst_b = L[11] & 0xffff;
@@ -460,8 +464,8 @@ extern "C" int b2s_halo_plan(int64_t ctx, const void* field, int elem_size, int 
       if (reach >= ((int64_t)1 << 31)) p.narrow = false;
     }
     if (L[8] * L[9] > p.max_strip) p.max_strip = (int)(L[8] * L[9]);
-    ((L[11] & kOut) ? out : in).push_back(n);
-    if (L[11] & (kOut | kPushed)) p.mixed = true;
+    ((L[11] & kOut) ? out : ((L[11] & kStaged) ? staged : in)).push_back(n);
+    if (L[11] & (kOut | kPushed | kStaged)) p.mixed = true;
   }
   auto key = [&](int x) { return (links[(size_t)x * 12 + 11] & 0xffff) * 2 + (links[(size_t)x * 12 + 10] != c->rank ? 1 : 0); };
   std::stable_sort(in.begin(), in.end(), [&](int x, int y) { return key(x) < key(y); });
@@ -517,6 +521,12 @@ extern "C" int b2s_halo_plan(int64_t ctx, const void* field, int elem_size, int 
       push_total[L[10]] += nk;
       p.wait_a |= 1ull << L[10];
     }
+    p.nrows1 = (int)(rows.size() / impl::kMixedWords);
+    for (int n : staged) {  // second phase: unpack what the peers delivered into this rank's staging area
+      const int64_t* L = links + (size_t)n * 12;
+      add_row(L, base_on(c->rank), base_on(c->rank), c->rank, false);
+      p.wait_d |= 1ull << L[10];
+    }
     p.nrows = (int)(rows.size() / impl::kMixedWords);
     B2S_CUDA(cudaMalloc(&p.push_total_dev, sizeof(int) * c->world), "b2s_halo_plan: cudaMalloc");
     B2S_CUDA(cudaMemcpy(p.push_total_dev, push_total.data(), sizeof(int) * c->world, cudaMemcpyHostToDevice), "b2s_halo_plan: cudaMemcpy");
@@ -553,7 +563,7 @@ static int launch_exchange(HaloCtx* c, int plan, int gated, cudaStream_t s) {
     impl::HaloXchg3 X;
     X.rows = p.rows_dev, X.peer_flags = c->peer_flags_dev, X.push_total = p.push_total_dev, X.state = c->state;
     X.wait_a = p.wait_a, X.wait_d = p.wait_d;
-    X.nrows = p.nrows, X.nk = p.nk, X.my_rank = c->rank, X.world = c->world;
+    X.nrows = p.nrows, X.nrows1 = p.nrows1, X.nk = p.nk, X.my_rank = c->rank, X.world = c->world;
     return impl::halo_exchange3_launch(p.elem_size, p.max_strip, X, s);
   }
   return impl::halo_exchange_launch(p.elem_size, p.nb, p.max_strip, xchg_of(c, p, gated), p.narrow, s);

@@ -281,6 +281,8 @@ struct HaloXchg3 {
   unsigned long long wait_a;  // ranks whose announcement is awaited: sources of pulls across GPUs and targets of pushes
   unsigned long long wait_d;  // ranks that push into this one
   int nrows, nk, my_rank, world;
+  int nrows1;                 // rows [0, nrows1) run before the deliveries are awaited, rows [nrows1, nrows) after (the
+                              // unpacking of what the peers delivered into this rank's staging buffer)
 };
 static constexpr int kMixedWords = 14;
 static constexpr int kPushWord = 320;
@@ -318,9 +320,11 @@ __device__ __forceinline__ void halo_exchange_body3(const HaloXchg3& X, int ku, 
   };
   bool announced = X.world <= 1 || X.wait_a == 0ull;
   if (blockIdx.x == 0 && threadIdx.x == 0) trace_ns(state, 0);
-  const int nk = X.nk, nchunks = (nk + ku - 1) / ku, units = X.nrows * nchunks;
+  const int nk = X.nk, nchunks = (nk + ku - 1) / ku;
+  auto run_rows = [&](int row0, int row1) {
+  const int units = (row1 - row0) * nchunks;
   for (int u = blockIdx.x; u < units; u += gridDim.x) {
-    const int row = u / nchunks, k0 = (u - row * nchunks) * ku;
+    const int row = row0 + u / nchunks, k0 = (u % nchunks) * ku;
     const int nlev = min(ku, nk - k0);
     const int64_t* L = table + (int64_t)row * kMixedWords;
     const int peer = (int)(L[11] & 0xffff) - 1;
@@ -366,8 +370,11 @@ __device__ __forceinline__ void halo_exchange_body3(const HaloXchg3& X, int ku, 
       }
     }
   }
+  };
+  run_rows(0, X.nrows1);
   if (!announced) await(X.wait_a, 0);
   if (X.wait_d != 0ull) await(X.wait_d, kDeliveredOffset);
+  run_rows(X.nrows1, X.nrows);  // same-GPU copies out of the staging buffer the peers have just filled
   // the last block of the launch advances the epoch for the next launch / graph replay
   __syncthreads();
   if (threadIdx.x == 0) {

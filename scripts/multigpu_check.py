@@ -45,7 +45,7 @@ def main():
         N, nk = 96, 5
         part = CubedSpherePartitioner(N, layout_for(world), corners=corners)
         nsub, ni, nj = part.subdomains_per_gpu(world), part.nx, part.ny
-        f = ctx.field((ni + 6, nj + 6, nk), nsub, torch.float64)
+        f = ctx.field((ni + 6, nj + 6, nk), nsub, torch.float64, part=part if corners else None)  # staged pushes with corners, in place without
         ex = ctx.plan(f, part)
         for rep in range(3):
             for b in range(nsub):
@@ -70,7 +70,7 @@ def main():
     nsub, ni, nj = part.subdomains_per_gpu(world), part.nx, part.ny
     g = torch.Generator(device=dev).manual_seed(7 + rank)
     mk = lambda s, lo, hi: fields.empty(s, torch.float64, dev, batch=nsub).uniform_(lo, hi, generator=g)  # noqa: E731
-    q = ctx.field((ni + 6, nj + 6, nk), nsub, torch.float64)
+    q = ctx.field((ni + 6, nj + 6, nk), nsub, torch.float64, part=part)
     q.uniform_(0.5, 1.5, generator=g)
     ex = ctx.plan(q, part)
     crx, cry = mk((ni + 1, nj, nk), -0.9, 0.9), mk((ni, nj + 1, nk), -0.9, 0.9)

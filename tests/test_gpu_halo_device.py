@@ -82,12 +82,14 @@ def _run_ranks(world, body):
 @pytest.mark.parametrize("n_gpus", [1, 2, 4, 8])
 @pytest.mark.parametrize("corners", [False, True])
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
-@pytest.mark.parametrize("push", [True, False])
+@pytest.mark.parametrize("push", ["staged", "inplace", False])
 def test_device_exchange_virtual_ranks(n_gpus, corners, dtype, push, monkeypatch):
     """b2s_halo_init .. exchange .. finalize with one thread per rank: rendezvous, symmetric allocation, handshake,
     epoch counter; every halo cell against geometry after each of three exchanges.  ``push``: the plan carries the
     outgoing strips, so the ungated exchanges (reps 0 and 2) pull the same-GPU strips and PUSH what crosses ranks
-    (announce / deliver flags, k_halo_exchange3); the forked exchange of rep 1 goes the same way.  Without: pull only."""
+    (announce / deliver flags, k_halo_exchange3) -- "staged": packed into the staging area behind the destination's field
+    and unpacked there, "inplace": straight into the halo cells; the forked exchange of rep 1 goes the same way.
+    False: pull only."""
     monkeypatch.setenv("B2S_RDV_TIMEOUT", "60")
     N, nk = 24, 3
     part = CubedSpherePartitioner(N, layout_for(n_gpus), corners=corners)
@@ -97,8 +99,8 @@ def test_device_exchange_virtual_ranks(n_gpus, corners, dtype, push, monkeypatch
     def body(rank):
         ctx = HaloContext(rank, n_gpus, 0, session)
         try:
-            f = ctx.field((part.nx + 6, part.ny + 6, nk), nsub, dtype)
-            ex = ctx.plan(f, part, push=push)
+            f = ctx.field((part.nx + 6, part.ny + 6, nk), nsub, dtype, part=part if push == "staged" else None)
+            ex = ctx.plan(f, part, push=bool(push))
             for rep in range(3):
                 for b in range(nsub):
                     f[b].copy_(torch.from_numpy(global_id_field(part, rank * nsub + b, nk)))
@@ -239,7 +241,7 @@ def test_gated_step_virtual_ranks(n_gpus, mode):
     def body(rank):
         ctx = HaloContext(rank, n_gpus, 0, session)
         try:
-            q = ctx.field((ni + 6, nj + 6, nk), nsub, dtype)
+            q = ctx.field((ni + 6, nj + 6, nk), nsub, dtype, part=part)
             q[:, 3:-3, 3:-3] = data[rank]["core"]
             ex = ctx.plan(q, part)
             tr = FvTransport(part, n_gpus, rank, exchange="device", halo_exchange=ex, overlap=mode != "serial", fused=fused)
