@@ -222,10 +222,10 @@ def main(argv=None) -> int:
                          "+ pull over NVLink peer memory, b2s_halo_*), forked next to a gated stencil launch; nccl = the "
                          "portable baseline: packed strips + grouped NCCL send/recv overlapped with an interior launch")
     ap.add_argument("--option", action="append", default=[], help="libb200stencil tuning option name=value (b2s_set_option), repeatable")
-    ap.add_argument("--push", choices=["staged", "inplace", "off"], default="staged",
-                    help="[serial step, N > 1] strips that cross NVLink: staged (default) = pushed PACKED by their owner into a staging "
-                         "area behind the destination's field and unpacked there; inplace = pushed straight into the halo cells; "
-                         "off = every strip pulled in place")
+    ap.add_argument("--push", choices=["staged", "inplace", "off"], default="off",
+                    help="[serial step, N > 1] strips that cross NVLink: off (default) = every strip pulled in place; staged = pushed "
+                         "PACKED by their owner into a staging area behind the destination's field and unpacked there; inplace = "
+                         "pushed straight into the halo cells (both measured slower than the pull: profiles/README.md, round 2)")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly (default: the step is replayed from a CUDA graph at every N)")
     ap.add_argument("--regions", type=int, default=0, help="timed regions of K steps each (median reported); 0 = auto")
     ap.add_argument("--fused-remap", action="store_true", help="[chain] fold pe_prefix into the remap kernel (remap_delp)")
@@ -294,8 +294,6 @@ def main(argv=None) -> int:
     # stencil; several GPUs -> the exchange forked beside ONE gated stencil launch (see AUTO_STEP_MODE)
     step_mode = "serial" if ns.no_overlap else (AUTO_STEP_MODE(n_gpus) if ns.step == "auto" else ns.step)
     stage_part = part if ns.push == "staged" else None  # reserve the staging area behind the exchanged fields
-    if ns.push == "off":
-        _abi.set_option("halo_push", 0)
 
     # ---- halo_check: the exchange the timed loop uses, on a global-id field, every halo cell against geometry ----
     halo_check = None
@@ -305,7 +303,7 @@ def main(argv=None) -> int:
         for b in range(nsub):
             idf[b].copy_(torch.from_numpy(global_id_field(part, rank * nsub + b, nk_chk)))
         barrier()
-        ex_chk = ctx.plan(idf, part)
+        ex_chk = ctx.plan(idf, part, push=ns.push != "off")
         for _ in range(2):
             ex_chk.update()
         torch.cuda.synchronize()
@@ -325,7 +323,7 @@ def main(argv=None) -> int:
     if use_device:
         q = ctx.field((ni + 6, nj + 6, NK), nsub, dtype, part=stage_part)
         q.uniform_(0.5, 1.5, generator=g)
-        ex = ctx.plan(q, part)
+        ex = ctx.plan(q, part, push=ns.push != "off")
         tr = FvTransport(part, n_gpus, rank, exchange="device", halo_exchange=ex, overlap=step_mode != "serial", fused=step_mode == "fused")
     else:
         q = mk((ni + 6, nj + 6, NK), 0.5, 1.5)

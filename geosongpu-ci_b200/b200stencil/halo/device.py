@@ -131,12 +131,16 @@ class HaloContext:
         return self._gate
 
     def plan(self, field: torch.Tensor, part: CubedSpherePartitioner, n_gpus: Optional[int] = None, gpu: Optional[int] = None,
-             ranks: Optional[Sequence[int]] = None, push: bool = True) -> "HaloExchange":
+             ranks: Optional[Sequence[int]] = None, push: bool = False) -> "HaloExchange":
         """Bind the links that fill this GPU's halos to ``field`` (a tensor returned by :meth:`field`).
 
         ``ranks[g]`` = session rank that hosts GPU ``g`` of the decomposition (default: identity).  ``push`` (every rank
-        alike): the table also carries this GPU's outgoing strips, so that the ungated exchange can push what crosses
-        NVLink instead of pulling it (:func:`build_plan_table`); gated and fused exchanges pull regardless."""
+        alike): the table also carries this GPU's outgoing strips, so that the ungated exchange pushes what crosses
+        NVLink instead of pulling it (:func:`build_plan_table`; packed, if :meth:`field` reserved a staging area);
+        gated and fused exchanges pull regardless.  Off by default: on 2 and 8 B200s the pushed exchanges measured
+        3 - 19 % SLOWER per step than the in-place pull (profiles/README.md, round 2) -- each rank's update then ends
+        only after every neighbour has started its own and delivered, a tighter coupling than the pull's single
+        announcement per neighbour."""
         n_gpus = self.world if n_gpus is None else n_gpus
         gpu = self.rank if gpu is None else gpu
         ranks = list(ranks) if ranks is not None else list(range(n_gpus))

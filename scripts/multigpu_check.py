@@ -46,7 +46,7 @@ def main():
         part = CubedSpherePartitioner(N, layout_for(world), corners=corners)
         nsub, ni, nj = part.subdomains_per_gpu(world), part.nx, part.ny
         f = ctx.field((ni + 6, nj + 6, nk), nsub, torch.float64, part=part if corners else None)  # staged pushes with corners, in place without
-        ex = ctx.plan(f, part)
+        ex = ctx.plan(f, part, push=True)  # ungated exchanges: same-GPU strips pulled, the rest pushed by their owner
         for rep in range(3):
             for b in range(nsub):
                 f[b].copy_(torch.from_numpy(global_id_field(part, rank * nsub + b, nk)))

@@ -243,7 +243,7 @@ def test_gated_step_virtual_ranks(n_gpus, mode):
         try:
             q = ctx.field((ni + 6, nj + 6, nk), nsub, dtype, part=part)
             q[:, 3:-3, 3:-3] = data[rank]["core"]
-            ex = ctx.plan(q, part)
+            ex = ctx.plan(q, part, push=True)  # the serial step pushes (staged) what crosses ranks; gated / fused pull
             tr = FvTransport(part, n_gpus, rank, exchange="device", halo_exchange=ex, overlap=mode != "serial", fused=fused)
             d = data[rank]
             torch.cuda.current_stream().synchronize()
