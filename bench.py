@@ -33,8 +33,13 @@ UNIT = "points/s"
 
 
 def AUTO_STEP_MODE(n_gpus: int) -> str:
-    """How --step auto launches the device-exchange step (measured: profiles/README.md, round 2)."""
-    return "serial" if n_gpus == 1 else "overlap"
+    """How --step auto launches the device-exchange step: exchange kernel, then the plain stencil, at every N.
+
+    Measured in round 2 (profiles/README.md): on one GPU every link is a same-GPU copy that competes with the stencil for
+    HBM, so forking it only slows both (545 against 533 us); on two GPUs the gated stencil starts later than the serial one
+    (307 against 292 us: the forked exchange gets two blocks per SM and sub-domain 0's third of it takes longer than the
+    whole exchange alone); on eight the two tie (112.6 against 112.7 us)."""
+    return "serial"
 
 
 def algorithmic_bytes_per_point(es: int) -> float:
@@ -215,7 +220,7 @@ def main(argv=None) -> int:
     ap.add_argument("--step", choices=["auto", "fused", "overlap", "serial"], default="auto",
                     help="how the device-exchange step is launched: fused = ONE kernel (b2s_halo_fv_tp2d: the stencil grid shares the "
                          "exchange among its CTAs first, then computes behind per-sub-domain gates); overlap = exchange kernel forked "
-                         "beside one gated stencil launch; serial = exchange kernel, then stencil; auto = serial on one GPU, overlap on several")
+                         "beside one gated stencil launch; serial = exchange kernel, then stencil; auto = serial (AUTO_STEP_MODE)")
     ap.add_argument("--no-overlap", action="store_true", help="same as --step serial (and no interior/frame overlap on the NCCL baseline)")
     ap.add_argument("--halo", choices=["auto", "device", "nccl"], default="auto",
                     help="halo exchange: device (= auto) the library-owned exchange, ONE kernel per update (neighbour handshake "
@@ -290,8 +295,6 @@ def main(argv=None) -> int:
     for opt in ns.option:
         name, val = opt.split("=")
         _abi.set_option(name, int(val))
-    # auto: one GPU hosts the whole cube, every link is a same-GPU copy and there is no latency to hide -> exchange, then
-    # stencil; several GPUs -> the exchange forked beside ONE gated stencil launch (see AUTO_STEP_MODE)
     step_mode = "serial" if ns.no_overlap else (AUTO_STEP_MODE(n_gpus) if ns.step == "auto" else ns.step)
     stage_part = part if ns.push == "staged" else None  # reserve the staging area behind the exchanged fields
 

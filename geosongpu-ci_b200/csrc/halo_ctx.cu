@@ -550,6 +550,7 @@ static impl::HaloXchg xchg_of(const HaloCtx* c, const Plan& p, int gated) {
   X.links = p.links_dev, X.peer_flags = c->peer_flags_dev, X.b_total = p.b_total_dev, X.state = c->state, X.dst = p.field;
   X.peers = p.peers;
   X.nlinks = p.nlinks, X.nk = p.nk, X.my_rank = c->rank, X.world = c->world, X.gated = gated;
+  X.single_wait = option("halo_handshake", 0) == 1 ? 1 : 0;
   return X;
 }
 

@@ -16,10 +16,12 @@ struct HaloXchg {
   void* dst;                  // this rank's field
   unsigned long long peers;   // bit r set: some link reads rank r's field (the ranks whose announcement is awaited)
   int nlinks, nk, my_rank, world, gated;
+  int single_wait;            // != 0: every block polls the peers' flags itself (the first form of the handshake wait)
 };
 
 static constexpr int kExchangeWords = 12;
 static constexpr long long kSyncTimeoutCycles = 4000000000LL;
+static constexpr int kReadyWord = 3;  // epoch for which block 0 has seen every awaited announcement (kHandshake 1)
 static constexpr int kDoneWord = 32;
 static constexpr int kGateWord = 128;
 static constexpr int kTraceWord = 200;  // uint64 timeline slots (tma.cuh gate_trace): [0] start, [1] end, [2] gate 0 opened
@@ -36,6 +38,11 @@ __device__ __forceinline__ int ld_relaxed_sys(const int* p) {
   asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ int ld_relaxed_gpu(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 // acquire / release fences (not the sequentially consistent __threadfence*: nothing here needs SC ordering)
 __device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
@@ -47,6 +54,48 @@ __device__ __forceinline__ void strip_decode(int t, int nd, int np, int64_t ssd,
   } else {
     p = t % np;
     d = t / np;
+  }
+}
+
+// Wait until every rank in `mask` has announced `epoch` (flag array at `offset`: 0 = announcements, 64 = deliveries).
+// Called by every thread of the block; contains block barriers.
+//   * block 0: one thread per awaited rank polls this GPU's own flag array with system-scope relaxed loads, one
+//     system-scope acquire fence each, then thread 0 publishes the epoch in state[ready_word] (release, GPU scope);
+//   * every other block: ONE thread polls that word (a GPU-scope load that hits this GPU's L2) and fences at GPU scope.
+// The first version had every block poll the flags and fence at system scope: up to seven MEMBAR.SYS per block, hundreds
+// of blocks hammering the very lines the peers' NVLink writes must land in.  The announcements happen-before block 0's
+// fence, which happens-before its release, which the other blocks acquire: their loads of peer memory are ordered
+// after the peers' writes by causality.  `single` (a plan option) keeps the per-block form for A/B runs.
+__device__ __forceinline__ void await_flags(const int64_t* peer_flags, int my_rank, int world, unsigned long long mask, int offset,
+                                            int epoch, int* state, int ready_word, bool single) {
+  const int nthreads = blockDim.x;
+  if (single || blockIdx.x == 0) {
+    for (int r = threadIdx.x; r < world; r += nthreads)
+      if ((mask >> r) & 1ull) {
+        const int* mine = reinterpret_cast<const int*>(static_cast<uintptr_t>(peer_flags[my_rank])) + offset + r;
+        const long long t0 = clock64();
+        while (ld_relaxed_sys(mine) < epoch) {
+          if (clock64() - t0 > kSyncTimeoutCycles) {
+            atomicExch(state + 2, 1);
+            break;
+          }
+        }
+        fence_acq_rel_sys();
+      }
+    __syncthreads();
+    if (!single && threadIdx.x == 0) st_release_gpu(state + ready_word, epoch);
+  } else {
+    if (threadIdx.x == 0) {
+      const long long t0 = clock64();
+      while (ld_relaxed_gpu(state + ready_word) < epoch) {
+        if (clock64() - t0 > kSyncTimeoutCycles) {
+          atomicExch(state + 2, 1);
+          break;
+        }
+      }
+      fence_acq_rel_gpu();
+    }
+    __syncthreads();
   }
 }
 
@@ -66,21 +115,8 @@ __device__ __forceinline__ void halo_exchange_body_inl(const HaloXchg& X, int* s
     if (blockIdx.x == 0)
       for (int r = threadIdx.x; r < X.world; r += nthreads)
         if (r != X.my_rank) st_release_sys(reinterpret_cast<int*>(static_cast<uintptr_t>(X.peer_flags[r])) + X.my_rank, epoch);
-    // ... and every block waits for the announcements of the ranks it may read, all at once: one thread per awaited
-    // peer polls its flag in this GPU's own memory (relaxed loads, no fence per poll), one acquire fence at the end
-    for (int r = threadIdx.x; r < X.world; r += nthreads)
-      if ((X.peers >> r) & 1ull) {
-        const int* mine = reinterpret_cast<const int*>(static_cast<uintptr_t>(X.peer_flags[X.my_rank])) + r;
-        const long long t0 = clock64();
-        while (ld_relaxed_sys(mine) < epoch) {
-          if (clock64() - t0 > kSyncTimeoutCycles) {
-            atomicExch(state + 2, 1);
-            break;
-          }
-        }
-        fence_acq_rel_sys();
-      }
-    __syncthreads();
+    // ... and every block waits until the announcements of all the ranks it may read have arrived (await_flags)
+    await_flags(X.peer_flags, X.my_rank, X.world, X.peers, 0, epoch, state, kReadyWord, X.single_wait != 0);
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) trace_ns(state, 0);
   const int nk = X.nk, units = X.nlinks * nk;
@@ -174,21 +210,10 @@ __device__ __forceinline__ void halo_exchange_body2(const HaloXchg& X, int ku, i
   bool awaited = X.world <= 1;
   // every awaited peer at once: one thread per peer polls this GPU's own flag array, one acquire fence at the end
   auto await_peers = [&]() {
-    for (int r = threadIdx.x; r < X.world; r += nthreads)
-      if ((X.peers >> r) & 1ull) {
-        const int* mine = reinterpret_cast<const int*>(static_cast<uintptr_t>(X.peer_flags[X.my_rank])) + r;
-        const long long t0 = clock64();
-        while (ld_relaxed_sys(mine) < epoch) {
-          if (clock64() - t0 > kSyncTimeoutCycles) {
-            atomicExch(state + 2, 1);
-            break;
-          }
-        }
-        fence_acq_rel_sys();
-      }
-    __syncthreads();
+    await_flags(X.peer_flags, X.my_rank, X.world, X.peers, 0, epoch, state, kReadyWord, X.single_wait != 0);
     awaited = true;
   };
+  if (!awaited && blockIdx.x == 0) await_peers();  // block 0 relays the announcements to the other blocks: at once
   if (blockIdx.x == 0 && threadIdx.x == 0) trace_ns(state, 0);
   const int nk = X.nk, nchunks = (nk + ku - 1) / ku, units = X.nlinks * nchunks;
   T* dst = static_cast<T*>(X.dst);
@@ -304,21 +329,13 @@ __device__ __forceinline__ void halo_exchange_body3(const HaloXchg3& X, int ku, 
       if (r != X.my_rank) st_release_sys(reinterpret_cast<int*>(static_cast<uintptr_t>(X.peer_flags[r])) + X.my_rank, epoch);
   // one thread per awaited rank polls this GPU's own flag array (A: offset 0, D: offset 64), one acquire fence each
   auto await = [&](unsigned long long mask, int offset) {
-    for (int r = threadIdx.x; r < X.world; r += nthreads)
-      if ((mask >> r) & 1ull) {
-        const int* mine = reinterpret_cast<const int*>(static_cast<uintptr_t>(X.peer_flags[X.my_rank])) + offset + r;
-        const long long t0 = clock64();
-        while (ld_relaxed_sys(mine) < epoch) {
-          if (clock64() - t0 > kSyncTimeoutCycles) {
-            atomicExch(state + 2, 1);
-            break;
-          }
-        }
-        fence_acq_rel_sys();
-      }
-    __syncthreads();
+    await_flags(X.peer_flags, X.my_rank, X.world, mask, offset, epoch, state, offset == 0 ? kReadyWord : kReadyWord + 1, false);
   };
   bool announced = X.world <= 1 || X.wait_a == 0ull;
+  if (!announced && blockIdx.x == 0) {  // block 0 relays the announcements to the other blocks: at once
+    await(X.wait_a, 0);
+    announced = true;
+  }
   if (blockIdx.x == 0 && threadIdx.x == 0) trace_ns(state, 0);
   const int nk = X.nk, nchunks = (nk + ku - 1) / ku;
   auto run_rows = [&](int row0, int row1) {

@@ -178,8 +178,7 @@ int halo_exchange3_launch(int elem_size, int max_strip, const HaloXchg3& X, cuda
   B2S_ARGCHECK(X.world >= 1 && X.world <= 64 && X.my_rank >= 0 && X.my_rank < X.world, "halo_exchange: rank %d of %d", X.my_rank, X.world);
   B2S_ARGCHECK(X.peer_flags && X.state && X.push_total && X.nk > 0 && X.nrows >= 0 && (X.nrows == 0 || X.rows), "halo_exchange: bad mixed plan");
   int ku = option("halo_levels_per_unit", 0);
-  if (ku <= 0 || ku > kMaxLevelsPerUnit) ku = (kLoadsInFlight * 256) / (max_strip > 0 ? max_strip : 1);
-  ku = ku < 1 ? 1 : (ku > kMaxLevelsPerUnit ? kMaxLevelsPerUnit : ku);
+  if (ku <= 0 || ku > kMaxLevelsPerUnit) ku = 1;
   if (ku > X.nk) ku = X.nk;
   int per_sm = option("halo_blocks_per_sm", 0);
   if (per_sm <= 0 || per_sm > 4) per_sm = 4;
@@ -247,13 +246,13 @@ int halo_exchange_launch(int elem_size, int nb, int max_strip, const HaloXchg& X
     return check_launch("halo_exchange");
   }
   // Version 2: a persistent grid walks the (link, chunk of ku levels) units in link order, so sub-domains complete -- and
-  // their gates open -- one after the other.  ku: as many levels as make a unit ONE batch of loads (256 threads x 8 in
-  // flight = 2048 elements: 3 levels of a 3 x 192 strip, 1 of a 3 x 384 strip).  Blocks per SM: 2 beside a gated stencil
-  // (thousands of blocks would take every thread slot and keep the stencil from becoming resident,
-  // profiles/r02_overlap.md), 4 (the register limit) alone on the stream.
+  // their gates open -- one after the other.  ku = 1 level per unit: filling a unit up to ONE batch of eight loads per
+  // thread (3 levels of a 3 x 192 strip) measured 2 % slower per step on 8 GPUs than one level per unit with three times
+  // the units (profiles/README.md, round 2); b2s_set_option("halo_levels_per_unit", n) for A/B runs.  Blocks per SM: 2
+  // beside a gated stencil (thousands of blocks would take every thread slot and keep the stencil from becoming
+  // resident, profiles/r02_overlap.md), 4 (the register limit) alone on the stream.
   int ku = option("halo_levels_per_unit", 0);
-  if (ku <= 0 || ku > kMaxLevelsPerUnit) ku = (kLoadsInFlight * 256) / (max_strip > 0 ? max_strip : 1);
-  ku = ku < 1 ? 1 : (ku > kMaxLevelsPerUnit ? kMaxLevelsPerUnit : ku);
+  if (ku <= 0 || ku > kMaxLevelsPerUnit) ku = 1;
   if (ku > X.nk) ku = X.nk;
   if (per_sm <= 0 || per_sm > 4) per_sm = X.gated ? 2 : 4;
   const int64_t slots = (int64_t)sm_count() * per_sm;
