@@ -93,8 +93,8 @@ int halo_move(int nlinks, int nk, int max_strip, const int64_t* links, const T* 
 static constexpr int kPullWords = 11;
 
 template <typename T, int KU>
-__global__ void __launch_bounds__(256) k_halo_pull(int nk, const int64_t* __restrict__ links, T* dst) {
-  const int64_t* L = links + (int64_t)blockIdx.z * kPullWords;
+__global__ void __launch_bounds__(256) k_halo_pull(int nk, const int64_t* __restrict__ links, T* dst, int words) {
+  const int64_t* L = links + (int64_t)blockIdx.z * words;
   const int nd = (int)L[8], np = (int)L[9];
   const int t = blockIdx.x * 256 + threadIdx.x;
   if (t >= nd * np) return;
@@ -114,9 +114,9 @@ int halo_pull(int nlinks, int nk, int max_strip, const int64_t* links, T* dst, c
   B2S_ARGCHECK(nk <= 65535 && nlinks <= 65535, "halo_pull: grid too large (nk=%d, nlinks=%d)", nk, nlinks);
   const int ku = halo_levels();
   dim3 grid((max_strip + 255) / 256, (nk + ku - 1) / ku, nlinks);
-  if (ku == 8) k_halo_pull<T, 8><<<grid, 256, 0, s>>>(nk, links, dst);
-  else if (ku == 4) k_halo_pull<T, 4><<<grid, 256, 0, s>>>(nk, links, dst);
-  else k_halo_pull<T, 1><<<grid, 256, 0, s>>>(nk, links, dst);
+  if (ku == 8) k_halo_pull<T, 8><<<grid, 256, 0, s>>>(nk, links, dst, kPullWords);
+  else if (ku == 4) k_halo_pull<T, 4><<<grid, 256, 0, s>>>(nk, links, dst, kPullWords);
+  else k_halo_pull<T, 1><<<grid, 256, 0, s>>>(nk, links, dst, kPullWords);
   return check_launch("halo_pull");
 }
 
@@ -192,6 +192,33 @@ int halo_exchange3_launch(int elem_size, int max_strip, const HaloXchg3& X, cuda
   return check_launch("halo_exchange");
 }
 
+// version 4 = the handshake as its OWN one-block kernel, then the plain flat-grid pull (k_halo_pull: one thread per strip
+// element, no flags, no fences, no epoch logic): two launches, each as simple as it gets.  The kernel boundary orders
+// the pull after the acquired announcements.  The single block also advances the epoch.
+__global__ void __launch_bounds__(64) k_halo_handshake(int my_rank, int world, const int64_t* __restrict__ peer_flags, unsigned long long peers,
+                                                       int* state) {
+  const int epoch = *reinterpret_cast<volatile int*>(state) + 1;
+  for (int r = threadIdx.x; r < world; r += blockDim.x)
+    if (r != my_rank) st_release_sys(reinterpret_cast<int*>(static_cast<uintptr_t>(peer_flags[r])) + my_rank, epoch);
+  for (int r = threadIdx.x; r < world; r += blockDim.x)
+    if ((peers >> r) & 1ull) {
+      const int* mine = reinterpret_cast<const int*>(static_cast<uintptr_t>(peer_flags[my_rank])) + r;
+      const long long t0 = clock64();
+      while (ld_relaxed_sys(mine) < epoch) {
+        if (clock64() - t0 > kSyncTimeoutCycles) {
+          atomicExch(state + 2, 1);
+          break;
+        }
+      }
+      fence_acq_rel_sys();
+    }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    trace_ns(state, 0);
+    *reinterpret_cast<volatile int*>(state) = epoch;
+  }
+}
+
 // an exchange without links still has to announce, advance the epoch and raise the gate
 __global__ void k_halo_exchange_empty(int my_rank, int world, const int64_t* __restrict__ peer_flags, int* state, int nb, int gated) {
   const int epoch = *reinterpret_cast<volatile int*>(state) + 1;
@@ -215,6 +242,9 @@ int halo_kernels_preload() {
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_halo_exchange2<float>);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_halo_exchange3<double>);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_halo_exchange3<float>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_halo_handshake);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_halo_pull<double, 1>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_halo_pull<float, 1>);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_halo_exchange_empty);
   if (e != cudaSuccess) return set_error((int)e, "halo exchange kernels: %s", cudaGetErrorString(e));
   return B2S_OK;
@@ -234,6 +264,22 @@ int halo_exchange_launch(int elem_size, int nb, int max_strip, const HaloXchg& X
   // forked version 2 made the overlapped step three times longer (0.9 ms against 0.31 ms) while the serial steps of the two
   // versions tied; its 64 registers per thread do not fit twice per SM beside three 160-thread stencil CTAs
   const int variant = option("halo_variant", 0);
+  if (variant == 4 && !X.gated) {
+    k_halo_handshake<<<1, 64, 0, s>>>(X.my_rank, X.world, X.peer_flags, X.peers, X.state);
+    if (int rc = check_launch("halo_exchange(handshake)")) return rc;
+    const int ku = halo_levels();
+    dim3 grid((max_strip + 255) / 256, (X.nk + ku - 1) / ku, X.nlinks);
+    if (elem_size == 8) {
+      if (ku == 8) k_halo_pull<double, 8><<<grid, 256, 0, s>>>(X.nk, X.links, static_cast<double*>(X.dst), kExchangeWords);
+      else if (ku == 4) k_halo_pull<double, 4><<<grid, 256, 0, s>>>(X.nk, X.links, static_cast<double*>(X.dst), kExchangeWords);
+      else k_halo_pull<double, 1><<<grid, 256, 0, s>>>(X.nk, X.links, static_cast<double*>(X.dst), kExchangeWords);
+    } else {
+      if (ku == 8) k_halo_pull<float, 8><<<grid, 256, 0, s>>>(X.nk, X.links, static_cast<float*>(X.dst), kExchangeWords);
+      else if (ku == 4) k_halo_pull<float, 4><<<grid, 256, 0, s>>>(X.nk, X.links, static_cast<float*>(X.dst), kExchangeWords);
+      else k_halo_pull<float, 1><<<grid, 256, 0, s>>>(X.nk, X.links, static_cast<float*>(X.dst), kExchangeWords);
+    }
+    return check_launch("halo_exchange(pull)");
+  }
   if (variant == 1 || (variant == 0 && X.gated) || !narrow) {
     // beside a gated stencil (forked exchange): 2 blocks x 256 threads x ~50 registers per SM leave room for four stencil
     // CTAs; alone on the GPU: every thread slot, the copy is bound by the number of (remote) loads in flight

@@ -6,7 +6,8 @@ both sides, max over ranks, median of the regions).  bench.py pays ~20 s of star
 that is what the GPU budget goes to.
 
 usage: torchrun --nproc-per-node N scripts/step_modes_probe.py [--steps 1000] [--regions 3] [--configs name,name,...]
-A configuration is  mode[:option=value[:option=value...]]  with mode = serial | overlap | fused.
+A configuration is  mode[:option=value[:option=value...]]  with mode = serial | overlap | fused, or one of the two halves
+of the serial step alone: stencil (no exchange: the slowest rank's kernel, free of the lock-step) | exchange.
 """
 import argparse
 import json
@@ -28,7 +29,7 @@ from b200stencil.halo.transport import FvTransport
 
 DEFAULT = ("serial,serial:halo_variant=1,serial:halo_levels_per_unit=1,serial:halo_blocks_per_sm=2,overlap,"
            "overlap:halo_blocks_per_sm=4,overlap:halo_variant=2,fused")
-OPTIONS = ("halo_variant", "halo_levels_per_unit", "halo_blocks_per_sm", "halo_push", "fv_variant")
+OPTIONS = ("halo_variant", "halo_levels_per_unit", "halo_blocks_per_sm", "halo_push", "halo_handshake", "halo_levels", "fv_variant")
 
 
 def main():
@@ -71,21 +72,23 @@ def main():
         for o in opts:
             k, v = o.split("=")
             _abi.set_option(k, int(v))
-        tr = FvTransport(part, world, rank, exchange="device", halo_exchange=ex, overlap=mode != "serial", fused=mode == "fused")
+        tr = FvTransport(part, world, rank, exchange="device", halo_exchange=ex, overlap=mode not in ("serial", "stencil", "exchange"),
+                         fused=mode == "fused")  # fmt: skip
+        step = {"stencil": tr.calls(*args)[0], "exchange": ex.update}.get(mode, lambda: tr.step(*args))
         for _ in range(5):
-            tr.step(*args)
+            step()
         barrier()
         ctx.check()
         same = True
-        if want is None:
+        if want is None and mode != "exchange":
             want = out.clone()
-        else:
+        elif mode != "exchange":
             same = bool(torch.equal(out, want))
         cap = torch.cuda.Stream(device=dev)
         cap.wait_stream(torch.cuda.current_stream(dev))
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph, stream=cap):
-            tr.step(*args)
+            step()
         for _ in range(3):
             graph.replay()
         barrier()

@@ -57,8 +57,18 @@ def test_halo_pull_virtual_peers(n_gpus, corners, dtype):
 
 
 def _run_ranks(world, body):
-    """One thread per virtual rank on cuda:0; re-raises the first failure."""
+    """One thread per virtual rank on cuda:0; re-raises the first failure.
+
+    The exchange kernels of ALL the virtual ranks must be resident on the one GPU at the same time (they wait for each
+    other), so the ranks take several levels per work unit: 8 ranks x (links x levels) blocks would not fit otherwise.
+    One rank per GPU -- the product configuration -- has the GPU to itself."""
     errors = []
+    if world > 1 and _abi.get_option("halo_levels_per_unit") == 0:
+        _abi.set_option("halo_levels_per_unit", 8)
+        try:
+            return _run_ranks(world, body)
+        finally:
+            _abi.set_option("halo_levels_per_unit", 0)
 
     def wrap(rank):
         try:
@@ -121,6 +131,41 @@ def test_device_exchange_virtual_ranks(n_gpus, corners, dtype, push, monkeypatch
             ctx.finalize()
 
     _run_ranks(n_gpus, body)
+
+
+@pytest.mark.parametrize("n_gpus", [2, 8])
+@pytest.mark.parametrize("option", [("halo_variant", 4), ("halo_variant", 1), ("halo_handshake", 1), ("halo_levels_per_unit", 3)])
+def test_exchange_variants_virtual_ranks(n_gpus, option):
+    """The pull exchange in its other forms (b2s_set_option): the one-block handshake kernel followed by the flat-grid pull,
+    the first version of the one-kernel exchange, the per-block handshake wait, several levels per work unit -- same halos."""
+    N, nk = 24, 2  # few levels: version 1 takes one block per (link, level), and all ranks' blocks must be co-resident
+    part = CubedSpherePartitioner(N, layout_for(n_gpus), corners=True)
+    nsub = part.subdomains_per_gpu(n_gpus)
+    session = uuid.uuid4().hex
+    _abi.set_option(*option)
+
+    def body(rank):
+        ctx = HaloContext(rank, n_gpus, 0, session)
+        try:
+            f = ctx.field((part.nx + 6, part.ny + 6, nk), nsub, torch.float64)
+            ex = ctx.plan(f, part)
+            for rep in range(3):
+                for b in range(nsub):
+                    f[b].copy_(torch.from_numpy(global_id_field(part, rank * nsub + b, nk)))
+                torch.cuda.current_stream().synchronize()
+                ctx.barrier()
+                ex.update()
+                torch.cuda.current_stream().synchronize()
+                _check(part, n_gpus, rank, f, nk)
+                ctx.barrier()
+            assert ctx.status() == (3, 0)
+        finally:
+            ctx.finalize()
+
+    try:
+        _run_ranks(n_gpus, body)
+    finally:
+        _abi.set_option(option[0], 0)
 
 
 def _fv_fields(nsub, ni, nj, nk, dtype, seed):
