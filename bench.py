@@ -7,7 +7,7 @@
 Workload (BASELINE.json configs[3], the configuration the headline target is quoted on):
 FV3-style horizontal finite-volume flux/advection stencil (fv_tp2d, 3-cell halo) on the C384 cubed
 sphere (6 tiles x 384 x 384 columns) x 72 levels, synthetic fields.  One STEP = halo update of q from
-the neighbouring sub-domains (ONE kernel: same-GPU copies, and at N > 1 a neighbour handshake + pull over NVLink
+the neighbouring sub-domains (library-owned exchange: same-GPU copies, and at N > 1 a neighbour handshake + pull over NVLink
 peer memory, overlapped with the cells of the stencil that read no halo) followed by fv_tp2d on every sub-domain the
 GPU hosts.  The domain is fixed, so scaling is STRONG.
 
@@ -223,7 +223,7 @@ def main(argv=None) -> int:
                          "beside one gated stencil launch; serial = exchange kernel, then stencil; auto = serial (AUTO_STEP_MODE)")
     ap.add_argument("--no-overlap", action="store_true", help="same as --step serial (and no interior/frame overlap on the NCCL baseline)")
     ap.add_argument("--halo", choices=["auto", "device", "nccl"], default="auto",
-                    help="halo exchange: device (= auto) the library-owned exchange, ONE kernel per update (neighbour handshake "
+                    help="halo exchange: device (= auto) the library-owned exchange (neighbour handshake "
                          "+ pull over NVLink peer memory, b2s_halo_*), forked next to a gated stencil launch; nccl = the "
                          "portable baseline: packed strips + grouped NCCL send/recv overlapped with an interior launch")
     ap.add_argument("--option", action="append", default=[], help="libb200stencil tuning option name=value (b2s_set_option), repeatable")
@@ -371,6 +371,10 @@ def main(argv=None) -> int:
         ctx.check()
 
     full_call = tr.calls(*args)[0]
+    launches_before = _abi.launch_count()
+    tr.step(*args)
+    launches_eager_step = _abi.launch_count() - launches_before  # kernels of libb200stencil per step (NCCL's own are not counted)
+    barrier()
 
     # The whole step (both streams, exchange included) is captured ONCE into a CUDA graph and replayed at every N
     # (N = 1 included: one launch mode for the whole scaling curve), so the host never paces the device.
@@ -427,10 +431,7 @@ def main(argv=None) -> int:
     if ex is not None:
         ctx.check()  # no device-side wait timed out during the timed regions
         halo_trace = ctx.trace()  # device timeline (ns) of the last timed step
-    if ex is not None:
-        launches_per_step = 1 if tr.fused else 2  # the fused step is one launch; else k_halo_exchange + fv_tp2d (gated or plain)
-    else:
-        launches_per_step = (1 if not tr.updater.plan.peers else 3) + (1 if not tr.overlap else 1 + len(tr.frame))
+    launches_per_step = launches_eager_step  # counted by the library (b2s_launch_count) over one eager step before the capture
     launches = regions * K * launches_per_step if graph is not None else _abi.launch_count() - launches0
     elapsed_ms = statistics.median(region_ms)
     ms_per_step = elapsed_ms / K
@@ -566,7 +567,7 @@ def main(argv=None) -> int:
                 "step_launch": (step_mode if ex is not None else "nccl"),
                 "halo_exchange": (("device, fused: ONE kernel per step (b2s_halo_fv_tp2d) -- neighbour handshake + pull over NVLink peer memory "
                                    "shared among the CTAs of the stencil grid, then fv_tp2d behind per-sub-domain gates" if tr.fused else
-                                   "device: one exchange launch (b2s_halo_*: neighbour handshake; same-GPU strips pulled, strips that cross NVLink "
+                                   "device: library-owned exchange (b2s_halo_*: a one-block handshake kernel -- announce, await the neighbours -- then the strip copies; same-GPU strips pulled, strips that cross NVLink "
                                    + {"staged": "pushed packed into the destination's staging area and unpacked there", "inplace": "pushed into the halo cells",
                                       "off": "pulled in place"}[ns.push if not tr.overlap else "off"] + ")"
                                    + (", forked beside one gated fv_tp2d launch (sub-domain b computed while the halos of b+1.. arrive)" if tr.overlap else ", then fv_tp2d"))

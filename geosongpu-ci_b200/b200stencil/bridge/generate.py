@@ -364,7 +364,9 @@ B2S_API int b2s_halo_peer_ptr(int64_t ctx, const void* ptr, int peer, void** pee
  * sub-domain (batch index of the field, < 64; 0 for an unbatched field). */
 B2S_API int b2s_halo_plan(int64_t ctx, const void* field, int elem_size, int nk, int nlinks, const int64_t* links, int* plan);
 B2S_API int64_t b2s_halo_plan_remote_bytes(int64_t ctx, int plan);
-/* halo update = ONE kernel (neighbour handshake + pull over peer memory).  b2s_halo_exchange runs it on `stream`;
+/* halo update.  b2s_halo_exchange runs it on `stream`: a one-block handshake kernel (announce this rank's field, await the
+ * neighbours' announcements) followed by the strip copies over peer memory (b2s_set_option("halo_variant", 1 | 2): ONE kernel with
+ * the handshake inside);
  * _start forks it onto the context's own high-priority stream (ordered after the work already on `stream`), _wait
  * joins: what the caller enqueues on `stream` in between overlaps the exchange.  Both can be captured in a CUDA graph.
  * gated != 0: the kernel opens gate[b] when the halos of sub-domain b are complete (b = 0, 1, ... in turn); exactly one

@@ -8,7 +8,8 @@ Rendezvous, peer mapping, the neighbour handshake and the pull all live behind t
 * wraps the symmetric allocation in a torch tensor (device storage only),
 * turns the partitioner's links into the host table ``b2s_halo_plan`` wants.
 
-A halo update is ONE kernel (handshake + pull).  ``start()`` forks it onto the context's own stream so it overlaps
+A halo update on the caller's stream is a one-block handshake kernel (announce, await the neighbours) followed by the
+strip copies; forked, it is ONE kernel with the handshake inside.  ``start()`` forks it onto the context's own stream so it overlaps
 whatever the caller launches before ``wait()``; with ``gated=True`` the kernel opens one gate per sub-domain as its
 halos land and a gated stencil (``stencils.prepare_fv_tp2d_gated``) computes sub-domain b while the halos of b+1..
 are still in flight.

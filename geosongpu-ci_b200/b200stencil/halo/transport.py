@@ -38,7 +38,7 @@ class FvTransport:
     """One transport step on this GPU's batch of sub-domains.
 
     ``exchange`` =
-      "device"  (the product path) the library-owned exchange of ``halo/device.py``: ONE kernel per halo update
+      "device"  (the product path) the library-owned exchange of ``halo/device.py``: a handshake kernel + the strip copies per halo update
                 (neighbour handshake + pull over NVLink peer memory).  ``q`` must be the field ``halo_exchange`` was
                 planned for (``HaloContext.field`` + ``HaloContext.plan``).  With ``overlap`` the exchange is forked onto
                 the context's stream and opens one gate per sub-domain as its halos land; ``fv_tp2d_gated`` walks the

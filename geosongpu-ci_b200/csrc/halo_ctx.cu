@@ -11,6 +11,7 @@
 //     (cudaIpc handles across processes, the raw pointer between threads of one process), so loads and stores on a
 //     peer address travel over NVLink / NVSwitch;
 //   * b2s_halo_plan: an affine link table (built on the host from the cubed-sphere connectivity) bound to a field;
+//   * b2s_halo_exchange: a one-block handshake kernel (announce, await the neighbours) + the flat-grid strip copies;
 //   * b2s_halo_exchange_start / _wait: ONE kernel per halo update (k_halo_exchange, csrc/k_halo.cu) that carries the
 //     neighbour handshake inside (release/acquire flags in peer memory, device-resident epoch, bounded waits), forked
 //     onto the context's high-priority stream so it overlaps the caller's interior compute; both calls can be captured
@@ -592,7 +593,7 @@ template int b2s::impl::halo_fv_tp2d<double>(int64_t, int, int, int, int, int, F
 template int b2s::impl::halo_fv_tp2d<float>(int64_t, int, int, int, int, int, F3<const float>, F3<const float>, F3<const float>,
                                             F3<const float>, F2<const float>, F3<float>, F3<float>, cudaStream_t);
 
-// Halo update of the plan's field on `stream` itself (no fork): handshake + pull in one kernel.
+// Halo update of the plan's field on `stream` itself (no fork): handshake kernel + pull kernel (halo_variant 1 | 2: one kernel).
 extern "C" int b2s_halo_exchange(int64_t ctx, int plan, void* stream) {
   B2S_CTX(c, ctx, "b2s_halo_exchange");
   DeviceGuard guard(c->device);

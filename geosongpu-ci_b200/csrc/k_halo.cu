@@ -260,11 +260,14 @@ int halo_exchange_launch(int elem_size, int nb, int max_strip, const HaloXchg& X
   B2S_ARGCHECK(X.nk > 0 && X.links && X.dst && X.b_total, "halo_exchange: bad sizes nlinks=%d nk=%d", X.nlinks, X.nk);
   const int64_t units1 = (int64_t)X.nlinks * X.nk;  // (link, level) strips
   int per_sm = option("halo_blocks_per_sm", 0);
-  // auto: version 2 alone on the stream; version 1 beside a gated stencil -- measured on two GPUs (C384x72, round 2) the
-  // forked version 2 made the overlapped step three times longer (0.9 ms against 0.31 ms) while the serial steps of the two
-  // versions tied; its 64 registers per thread do not fit twice per SM beside three 160-thread stencil CTAs
+  // beside a gated stencil: version 1 -- measured on two GPUs (C384x72, round 2) the forked version 2 made the overlapped
+  // step three times longer (0.9 ms against 0.31 ms); its 64 registers per thread do not fit twice per SM beside three
+  // 160-thread stencil CTAs
+  // auto: alone on the stream -> version 4, the one-block handshake kernel followed by the flat-grid pull (on 8 GPUs
+  // 93.5 us per step against 96.4 / 98.3 us for the one-kernel versions 1 / 2, and against 113 - 115 us before the handshake
+  // wait was relayed by block 0: profiles/README.md, round 2); beside a gated stencil -> version 1 (below)
   const int variant = option("halo_variant", 0);
-  if (variant == 4 && !X.gated) {
+  if ((variant == 4 || variant == 0) && !X.gated) {
     k_halo_handshake<<<1, 64, 0, s>>>(X.my_rank, X.world, X.peer_flags, X.peers, X.state);
     if (int rc = check_launch("halo_exchange(handshake)")) return rc;
     const int ku = halo_levels();

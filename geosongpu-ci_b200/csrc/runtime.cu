@@ -37,7 +37,7 @@ static std::map<std::string, int> g_options = {
     {"fv_split_rp", 0},     // streaming kernel: rows per barrier pair, 0 auto (2), 1 | 2
     {"halo_levels", 0},     // halo_move / halo_pull: levels per thread, 0 auto (1), 1 | 4 | 8 (k_halo.cu)
     {"halo_blocks_per_sm", 0}, // k_halo_exchange: resident blocks per SM of the persistent grid, 0 auto (2), 1 .. 8
-    {"halo_variant", 0},       // pull exchange: 0 auto (2 alone on the stream, 1 beside a gated stencil), 1 first version (table in global memory, 4 loads in flight), 2 (table in shared memory, 8 loads in flight), 4 = one-block handshake kernel + flat-grid pull (two launches)
+    {"halo_variant", 0},       // pull exchange: 0 auto (4 alone on the stream, 1 beside a gated stencil), 1 first one-kernel version (table in global memory, 4 loads in flight), 2 (table in shared memory, 8 loads in flight), 4 = one-block handshake kernel + flat-grid pull (two launches)
     {"halo_levels_per_unit", 0}, // k_halo_exchange2 / 3: levels per work unit, 0 auto
     {"halo_handshake", 0},     // wait for the neighbours' announcements: 0 = block 0 polls the peers' flags and relays through a local word, 1 = every block polls them (first form)
     {"halo_push", 1},          // ungated exchange of a plan that carries outgoing links: 1 = strips that cross NVLink are pushed by their owner (k_halo_exchange3), 0 = everything pulled; must be the same on every rank
