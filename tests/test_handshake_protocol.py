@@ -1,10 +1,11 @@
-"""Model check of the neighbour handshake of halo_pull_sync (csrc/k_halo.cu, experimental one-launch exchange).
+"""Model check of the neighbour handshakes of the library-owned halo exchange (csrc/halo_device.cuh, csrc/k_halo.cu):
+the pull protocol first, the push protocol of the mixed exchange below.
 
-The kernel cannot be run on several GPUs in this container, but its PROTOCOL can be executed: every rank is a
+The kernels cannot be run on several GPUs in this container, but their PROTOCOL can be executed: every rank is a
 sequence of micro-operations, a random scheduler interleaves the ranks, and the invariants a ping-pong time loop
 needs are asserted on every read and write:
 
-  step n of rank r:   announce   flags[p][r] = n for every neighbour p        (st.release.sys in block (0,0,0))
+  step n of rank r:   announce   flags[p][r] = n for every neighbour p        (st.release.sys, handshake kernel / block 0)
                       pull       for every link: wait flags[r][p] >= n, then read p's field      (ld.acquire.sys)
                       compute    write field version n into the OTHER buffer                      (the stencil)
 
