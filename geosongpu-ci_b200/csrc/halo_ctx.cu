@@ -299,9 +299,16 @@ extern "C" int b2s_halo_init(const char* session, int rank, int world, int devic
     close(fd);
     if (m == MAP_FAILED) return bail(set_error(B2S_ENOTINIT, "b2s_halo_init: mmap(%s): %s", c->shm_name.c_str(), strerror(errno)));
     c->seg = static_cast<Segment*>(m);  // a fresh segment is zero-filled, which is the initial state of every field
+    uint32_t seen = 0;
+    if (c->seg->magic.compare_exchange_strong(seen, kMagic, std::memory_order_acq_rel))
+      c->seg->world = (uint32_t)world;  // the first rank to arrive stamps the segment
+    else if (seen != kMagic)
+      return bail(set_error(B2S_ENOTINIT, "b2s_halo_init: shared-memory object %s exists and is not a b2s rendezvous segment", c->shm_name.c_str()));
     c->seg->attached.fetch_add(1, std::memory_order_acq_rel);
     int rc = rdv_barrier(c, "b2s_halo_init");
     if (rc) return bail(rc);
+    if (c->seg->world != (uint32_t)world)
+      return bail(set_error(B2S_EINVAL, "b2s_halo_init: session '%s' was opened for %u ranks, rank %d says %d", c->session.c_str(), c->seg->world, rank, world));
     if (rank == 0) shm_unlink(c->shm_name.c_str());  // every rank holds a mapping now; the name can go
   }
   int lo = 0, hi = 0;
@@ -485,12 +492,18 @@ extern "C" int b2s_halo_plan(int64_t ctx, const void* field, int elem_size, int 
     if (dst_b + 1 > p.nb) p.nb = (int)dst_b + 1;
   }
   for (int& v : per_b) v *= nk;  // work units (link, level) per destination sub-domain
-  B2S_CUDA(cudaMalloc(&p.b_total_dev, kGateSlots * sizeof(int)), "b2s_halo_plan: cudaMalloc");
-  B2S_CUDA(cudaMemcpy(p.b_total_dev, per_b.data(), kGateSlots * sizeof(int), cudaMemcpyHostToDevice), "b2s_halo_plan: cudaMemcpy");
-  if (!tbl.empty()) {
-    B2S_CUDA(cudaMalloc(&p.links_dev, tbl.size() * sizeof(int64_t)), "b2s_halo_plan: cudaMalloc");
-    B2S_CUDA(cudaMemcpy(p.links_dev, tbl.data(), tbl.size() * sizeof(int64_t), cudaMemcpyHostToDevice), "b2s_halo_plan: cudaMemcpy");
-  }
+  // host table -> device; a failure frees what this plan has allocated so far
+  auto upload = [&](auto** dev, const auto* host, size_t count) -> int {
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(dev), count * sizeof(**dev));
+    if (e == cudaSuccess) e = cudaMemcpy(*dev, host, count * sizeof(**dev), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) return B2S_OK;
+    for (void* q : {(void*)p.b_total_dev, (void*)p.links_dev, (void*)p.push_total_dev, (void*)p.rows_dev})
+      if (q) cudaFree(q);
+    return set_error((int)e, "b2s_halo_plan: %s", cudaGetErrorString(e));
+  };
+  if (int rc = upload(&p.b_total_dev, per_b.data(), (size_t)kGateSlots)) return rc;
+  if (!tbl.empty())
+    if (int rc = upload(&p.links_dev, tbl.data(), tbl.size())) return rc;
   if (p.mixed) {
     // mixed table: incoming strips that are not pushed (pulled: same-GPU ones first, they need no announcement), then the
     // outgoing strips (pushed), grouped by destination rank so that the delivery flags go out one rank after the other
@@ -529,12 +542,9 @@ extern "C" int b2s_halo_plan(int64_t ctx, const void* field, int elem_size, int 
       p.wait_d |= 1ull << L[10];
     }
     p.nrows = (int)(rows.size() / impl::kMixedWords);
-    B2S_CUDA(cudaMalloc(&p.push_total_dev, sizeof(int) * c->world), "b2s_halo_plan: cudaMalloc");
-    B2S_CUDA(cudaMemcpy(p.push_total_dev, push_total.data(), sizeof(int) * c->world, cudaMemcpyHostToDevice), "b2s_halo_plan: cudaMemcpy");
-    if (!rows.empty()) {
-      B2S_CUDA(cudaMalloc(&p.rows_dev, rows.size() * sizeof(int64_t)), "b2s_halo_plan: cudaMalloc");
-      B2S_CUDA(cudaMemcpy(p.rows_dev, rows.data(), rows.size() * sizeof(int64_t), cudaMemcpyHostToDevice), "b2s_halo_plan: cudaMemcpy");
-    }
+    if (int rc = upload(&p.push_total_dev, push_total.data(), (size_t)c->world)) return rc;
+    if (!rows.empty())
+      if (int rc = upload(&p.rows_dev, rows.data(), rows.size())) return rc;
   }
   c->plans.push_back(p);
   *plan_out = (int)c->plans.size() - 1;
