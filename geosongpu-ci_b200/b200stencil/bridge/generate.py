@@ -361,7 +361,16 @@ B2S_API int b2s_halo_free(int64_t ctx, void* ptr);
 B2S_API int b2s_halo_peer_ptr(int64_t ctx, const void* ptr, int peer, void** peer_ptr);
 /* bind a link table to a field.  links: HOST int64[nlinks][12]; words 0..9 as for b2s_halo_move (element offsets
  * relative to `field`, the same on every rank), [10] = rank that owns the source sub-domain, [11] = destination
- * sub-domain (batch index of the field, < 64; 0 for an unbatched field). */
+ * sub-domain (batch index of the field, < 64; 0 for an unbatched field) in its low 16 bits.
+ * Optional marks in word [11], for the push path of the ungated exchange (both ends of a strip must be marked alike on
+ * their ranks; gated and fused exchanges pull every incoming strip in place, marked or not):
+ *   B2S_HALO_LINK_OUT     the row is an OUTGOING strip: its source is on this rank, [10] = rank that owns the destination;
+ *   B2S_HALO_LINK_PUSHED  an incoming strip its owner pushes (the owner's table has the matching OUT row);
+ *   B2S_HALO_LINK_STAGED  a same-rank copy to run AFTER the deliveries of rank [10]: the owner pushed the strip, packed,
+ *                         into a staging area of this rank's allocation (the OUT row's destination); this row unpacks it. */
+#define B2S_HALO_LINK_OUT ((int64_t)1 << 32)
+#define B2S_HALO_LINK_PUSHED ((int64_t)1 << 33)
+#define B2S_HALO_LINK_STAGED ((int64_t)1 << 34)
 B2S_API int b2s_halo_plan(int64_t ctx, const void* field, int elem_size, int nk, int nlinks, const int64_t* links, int* plan);
 B2S_API int64_t b2s_halo_plan_remote_bytes(int64_t ctx, int plan);
 /* halo update.  b2s_halo_exchange runs it on `stream`: a one-block handshake kernel (announce this rank's field, await the
