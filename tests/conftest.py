@@ -34,7 +34,19 @@ def _has_cuda() -> bool:
         return False
 
 
+# Tests in which several ranks share ONE GPU and wait for each other ON THE DEVICE (virtual ranks: threads, or the
+# compiled C callers).  They depend on every rank's kernels being co-resident -- a property of the test set-up, not of the
+# product (one rank per GPU) -- so they run after everything else: the driver runs the suite with -x, and a stall there
+# must not keep the parity tests from being run and counted.
+_DEVICE_WAIT_TESTS = ("test_gpu_halo_device.py", "test_c_abi_driver.py::test_halo_lifecycle_from_c",
+                      "test_c_abi_driver.py::test_fortran_call_sequence_on_the_device")
+
+
 def pytest_collection_modifyitems(config, items):
+    last = [it for it in items if any(tag in it.nodeid for tag in _DEVICE_WAIT_TESTS)]
+    if last:
+        keep = [it for it in items if not any(tag in it.nodeid for tag in _DEVICE_WAIT_TESTS)]
+        items[:] = keep + last
     if _has_cuda():
         return
     skip = pytest.mark.skip(reason="no CUDA device in this container")
