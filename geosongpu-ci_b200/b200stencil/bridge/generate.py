@@ -30,6 +30,7 @@ DEFAULT_HEADER = os.path.join(REPO_ROOT, "include", "b200stencil.h")
 DEFAULT_GLUE = os.path.abspath(os.path.join(HERE, "..", "..", "csrc", "abi_glue.inc"))
 DEFAULT_FORTRAN = os.path.join(REPO_ROOT, "include", "b2s_interface_mod.f90")
 DEFAULT_FORTRAN_EXAMPLE = os.path.join(REPO_ROOT, "include", "b2s_example.f90")
+DEFAULT_CMAKE = os.path.join(REPO_ROOT, "include", "CMakeLists_partial.txt")
 
 PRECISIONS = {"double": ("double", "int64_t", ""), "float": ("float", "int32_t", "_f32")}
 
@@ -230,6 +231,57 @@ class Bridge:
 
         return fortran.emit_example_program(self)
 
+    def emit_cmake(self) -> str:
+        """``CMakeLists_partial.txt``: the build hint the reference generator drops beside its bridge
+        (cli.py:66-77 ``Build.generate_cmake``, templates/cmake.jinja2, with its [ADAPT] / [COPY] convention).
+
+        There the partial builds a CFFI library out of Python at configure time and needs MPI and an interpreter; here the
+        stencils already ARE a shared library, so the partial declares it as an IMPORTED target with the generated header's
+        directory, names the generated Fortran module as a source to append, and needs nothing else."""
+        P = self.prefix.upper()
+        return f"""# GENERATED by b200stencil/bridge/generate.py from b200stencil.yaml -- do not edit.
+# [ADAPT] comments point to lines to adapt in your CMakeLists.txt, [COPY] is code to copy as it stands
+# (the convention of the reference generator's hint, src/tcn/py_ftn_interface/templates/cmake.jinja2).
+
+#
+## [ADAPT] Where the repository (or an installed copy of include/ and lib/) lives.
+#
+
+if(NOT DEFINED {P}_ROOT)
+  get_filename_component({P}_ROOT "${{CMAKE_CURRENT_LIST_DIR}}/.." ABSOLUTE)
+endif()
+set({P}_INCLUDE_DIR "${{{P}_ROOT}}/include" CACHE PATH "directory of b200stencil.h and b2s_interface_mod.f90")
+set({P}_LIBRARY "${{{P}_ROOT}}/geosongpu-ci_b200/b200stencil/lib/libb200stencil.so" CACHE FILEPATH "the C-ABI library")
+
+#
+## [COPY] {self.prefix} interface: the C-ABI library as an imported target.
+#
+
+message(STATUS "Using the {self.prefix} stencil library: ${{{P}_LIBRARY}}")
+if(NOT EXISTS "${{{P}_LIBRARY}}")
+  message(SEND_ERROR "libb200stencil.so is not built: run python __graft_entry__.py in ${{{P}_ROOT}}")
+endif()
+add_definitions(-DRUN_{self.prefix})
+add_library({self.prefix}_interface SHARED IMPORTED GLOBAL)
+set_target_properties({self.prefix}_interface PROPERTIES
+  IMPORTED_LOCATION "${{{P}_LIBRARY}}"
+  IMPORTED_NO_SONAME TRUE
+  INTERFACE_INCLUDE_DIRECTORIES "${{{P}_INCLUDE_DIR}}")
+
+# Fortran callers compile the generated bind(c) module with their own sources
+set({self.prefix}_interface_sources "${{{P}_INCLUDE_DIR}}/b2s_interface_mod.f90")
+# [ADAPT] : use this to append the interface source to your program
+# list( APPEND sources ${{{self.prefix}_interface_sources}} )
+
+#
+## [ADAPT] Executable.
+#
+
+# [ADAPT] link your target against the interface (a device pointer and a cudaStream_t are all it takes from CUDA;
+# callers that allocate through the CUDA runtime also link CUDA::cudart)
+#target_link_libraries(test {self.prefix}_interface)
+"""
+
 
 RUNTIME_SYMBOLS = [
     "b2s_init",
@@ -407,6 +459,7 @@ def main(argv=None) -> int:
     ap.add_argument("--glue", default=DEFAULT_GLUE)
     ap.add_argument("--fortran", default=DEFAULT_FORTRAN)
     ap.add_argument("--fortran-example", default=DEFAULT_FORTRAN_EXAMPLE)
+    ap.add_argument("--cmake", default=DEFAULT_CMAKE, help="build hint (CMakeLists_partial.txt); empty to skip")
     ap.add_argument("--check", action="store_true", help="fail if the header on disk is stale")
     ns = ap.parse_args(argv)
     bridge = Bridge.from_yaml(ns.definition)
@@ -425,6 +478,9 @@ def main(argv=None) -> int:
     if ns.fortran_example:
         with open(ns.fortran_example, "w") as f:
             f.write(bridge.emit_fortran_example())
+    if ns.cmake:
+        with open(ns.cmake, "w") as f:
+            f.write(bridge.emit_cmake())
     return 0
 
 

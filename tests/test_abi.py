@@ -153,6 +153,41 @@ def test_fortran_checker_catches_defects(bridge, mutation, message):
     assert message in str(e.value), str(e.value)
 
 
+def test_cmake_partial_builds_the_c_acceptance_program(bridge, tmp_path):
+    """The build hint of the bridge (reference: cli.py:66-77 + templates/cmake.jinja2, "meant as a hint") is current and,
+    unlike the reference's, is exercised: a CMake project that includes it builds tests/c_abi/abi_driver.c against the
+    imported target, and the program fails loudly at b2s_init where there is no GPU."""
+    import shutil
+
+    with open(generate.DEFAULT_CMAKE) as f:
+        assert f.read() == bridge.emit_cmake(), "include/CMakeLists_partial.txt is stale: run python -m b200stencil.bridge.generate"
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    if shutil.which("cmake") is None or shutil.which("gcc") is None or not os.path.exists(os.path.join(cuda, "include", "cuda_runtime_api.h")):
+        pytest.skip("cmake, gcc or the CUDA runtime headers are not available")
+    (tmp_path / "CMakeLists.txt").write_text(
+        "cmake_minimum_required(VERSION 3.18)\nproject(b2s_accept C)\n"
+        f"include({generate.DEFAULT_CMAKE})\n"
+        f"add_executable(abi_driver {os.path.join(ROOT, 'tests', 'c_abi', 'abi_driver.c')})\n"
+        f"target_include_directories(abi_driver PRIVATE {cuda}/include)\n"
+        f"target_link_libraries(abi_driver b2s_interface {cuda}/lib64/libcudart.so)\n"
+    )
+    build = tmp_path / "build"
+    for cmd in (["cmake", "-S", str(tmp_path), "-B", str(build)], ["cmake", "--build", str(build)]):
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
+    exe = build / "abi_driver"
+    assert exe.exists()
+    try:
+        import torch
+
+        if torch.cuda.is_available():
+            return  # the program's run on the device is tests/test_c_abi_driver.py
+    except ImportError:
+        pass
+    run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert run.returncode != 0 and "no CPU fallback" in run.stdout + run.stderr
+
+
 def test_missing_library_is_loud(monkeypatch, tmp_path):
     monkeypatch.setattr(_abi, "LIB_PATH", str(tmp_path / "nope.so"))
     monkeypatch.setattr(_abi, "_state", {})
